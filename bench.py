@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the channelize-and-demodulate hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--seconds S]
+
+Workload (BASELINE.json configs[1]): SDR++-style int16 baseband capture, 10 MS/s, 60 s,
+5 NFM targets batched, de-emphasis 300 us, reference chunk 4 194 304 (tune_chunk_size).
+One "step" = one pass of the whole capture through the hot path:
+  value : capture already resident in HBM, `ChannelBank.process_resident` (device timed)
+  e2e   : capture in pinned HOST memory, streamed chunk by chunk through
+          `ChannelBank.process_chunk` (the reference loop body), H2D of every chunk and
+          D2H of every audio block inside the timed region
+N > 1 (torchrun): the capture is N x 60 s, time-sharded -- rank r owns seconds [60 r, 60 (r+1))
+with a filter-length halo and a recurrence warm-up; only audio is gathered to rank 0 (NCCL).
+
+`--impl reference` times the CPU restatement of the reference path (oracle/iq_oracle.py; the
+reference is pure Python and cannot travel to the GPU box) on a bounded sample, one process
+per target in parallel.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FS = 10e6
+SECONDS = 60.0
+OFFSETS = [-3.2e6, -1.1e6, 0.4e6, 2.3e6, 4.1e6]
+BW = 12_500.0
+DEEMPH_US = 300.0
+REQ_CHUNK = 1_048_576
+METRIC = "input complex Msamples/s"
+UNIT = "Msamples/s"
+
+
+def workload_name(seconds: float) -> str:
+    return f"cfg2: int16 IQ, 10 MS/s, {seconds:g} s, 5 NFM targets batched, deemph 300 us"
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic capture: 5 FM carriers + AWGN, int16 interleaved
+# ------------------------------------------------------------------------------------------
+def synth_capture_device(n0: int, n: int, device, seed: int):
+    """int16 [2*n] on `device` for global sample indices [n0, n0+n): carriers are functions of the
+    global index (float64 phase), noise is seeded per call."""
+    import torch
+    out = torch.empty(2 * n, dtype=torch.int16, device=device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    step = 1 << 23
+    two_pi = 2.0 * np.pi
+    for s in range(0, n, step):
+        m = min(step, n - s)
+        t = (torch.arange(m, device=device, dtype=torch.float64) + float(n0 + s)) / FS
+        re = torch.zeros(m, device=device, dtype=torch.float64)
+        im = torch.zeros(m, device=device, dtype=torch.float64)
+        for i, off in enumerate(OFFSETS):
+            tone = 700.0 + 150.0 * i
+            ph = two_pi * off * t + (2500.0 / tone) * torch.sin(two_pi * tone * t)
+            ph = torch.remainder(ph, two_pi)
+            re += 0.12 * torch.cos(ph)
+            im += 0.12 * torch.sin(ph)
+        noise = torch.randn((m, 2), device=device, dtype=torch.float32, generator=gen) * 0.02
+        iq = torch.stack((re.float() + noise[:, 0], im.float() + noise[:, 1]), dim=1).clamp_(-0.999, 0.999)
+        out[2 * s:2 * (s + m)] = torch.round(iq * 32767.0).to(torch.int16).reshape(-1)
+    return out
+
+
+def make_targets():
+    from iq_to_audio_b200.bank import Target
+    from iq_to_audio_b200.processing import channel_decimation, design_channel_filter
+    d, fs_ch = channel_decimation(FS, 96_000.0)
+    taps = design_channel_filter(FS, BW, d)
+    return d, fs_ch, [Target(o, taps, 1, "nfm", DEEMPH_US, True) for o in OFFSETS]
+
+
+# ------------------------------------------------------------------------------------------
+# clocks / throttle reasons during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period: float = 0.02):
+        self.period = period
+        self.samples: list[int] = []
+        self.reasons: set[str] = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if bit and (mask & bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+
+    def summary(self) -> dict:
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop (processing.py:1070-1154)
+# ------------------------------------------------------------------------------------------
+def _cpu_one_target(args):
+    raw, off, chunk = args
+    from oracle import iq_oracle as orc
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    plan = orc.TargetPlan(sample_rate=FS, freq_offset=off, bandwidth=BW, mode="nfm", deemph_us=DEEMPH_US,
+                          filter_block=65_536, mix_sign=1)
+    t0 = time.perf_counter()
+    res = orc.run_target(x, plan, chunk)
+    return time.perf_counter() - t0, int(res.audio.size)
+
+
+def cpu_sample_raw(n: int) -> np.ndarray:
+    from oracle import iq_oracle as orc
+    carriers = [dict(offset=o, amp=0.12, kind="fm", tone=700.0 + 150.0 * i, dev=2500.0) for i, o in enumerate(OFFSETS)]
+    return orc.to_s16(orc.multi_carrier_capture(FS, n, carriers))
+
+
+def cpu_run(n_frames: int, chunk: int, parallel: bool) -> tuple[float, int]:
+    """(seconds, processes used) for all 5 targets over n_frames of the capture."""
+    raw = cpu_sample_raw(n_frames)
+    jobs = [(raw, off, chunk) for off in OFFSETS]
+    if parallel:
+        import multiprocessing as mp
+        procs = max(1, min(len(jobs), os.cpu_count() or 1))
+        with mp.get_context("fork").Pool(procs) as pool:
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_target, jobs)
+            return time.perf_counter() - t0, procs
+    total = 0.0
+    for j in jobs:       # as shipped: targets one after another (cli.py:683-710)
+        dt, _ = _cpu_one_target(j)
+        total += dt
+    return total, 1
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seconds", type=float, default=SECONDS, help="capture length per GPU (default 60 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    steps = max(args.steps, 1)
+
+    from iq_to_audio_b200.processing import tune_chunk_size
+    chunk = tune_chunk_size(FS, REQ_CHUNK)
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_chunks = 2
+        n = n_chunks * chunk
+        times = []
+        procs = 1
+        for _ in range(warmup):
+            cpu_run(chunk // 4, chunk, True)
+        for _ in range(steps):
+            dt, procs = cpu_run(n, chunk, True)
+            times.append(dt)
+        dt = float(np.mean(times))
+        val = n / dt / 1e6
+        sample = f"first {n_chunks} chunks ({n} samples) of the workload per step, one process per target"
+        line = {
+            "metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 transforms / f32 audio (numpy+scipy)", "data": "synthetic",
+            "config": {"workload": workload_name(args.seconds), "chunk": chunk, "filter_block": 65_536},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from iq_to_audio_b200.bank import ChannelBank
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_seg = int(round(FS * args.seconds))
+    n_seg = (n_seg // chunk) * chunk if n_seg >= chunk else n_seg     # segments start on the reference chunk grid
+    d, fs_ch, targets = make_targets()
+    bank = ChannelBank(FS, d, targets, codec="pcm_s16le", iq_order="iq", ref_chunk=chunk, device=local_rank)
+    warm_rows = 600 if rank > 0 else 0                               # de-emphasis settles to < 1e-9
+    seg_begin = rank * n_seg
+    seg_end = seg_begin + n_seg
+    first = max(0, seg_begin - bank.halo - (warm_rows + 1) * d)
+    capture = synth_capture_device(first, seg_end - first, dev, seed=1234 + rank)
+    rows = bank.rows_in(seg_begin, seg_end)
+    audio = torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(audio) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def resident_step():
+        bank.process_resident(capture.data_ptr(), first, seg_end - first, seg_begin, seg_end,
+                              warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
+        if world > 1:
+            dist.gather(audio, gathered, dst=0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        resident_step()
+    sync_all()
+    bank.set_timing(True)
+    launches0 = bank.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            resident_step()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    # the bank launches on its own stream: the wall clock bracketed by synchronize is the step time;
+    # the CUDA events on torch's stream only bound the gather
+    step_ms = max(dev_ms, wall * 1e3) / steps
+    timing = bank.get_timing()
+    launches = bank.launches - launches0
+    bank.set_timing(False)
+    sync_all()
+    if world > 1:
+        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+
+    # ---- e2e: pinned host capture streamed through process_chunk -----------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(2 * n_seg, dtype=torch.int16).pin_memory()
+        host.copy_(capture[2 * (seg_begin - first):])
+        host_np = host.numpy()
+        nchunks = (n_seg + chunk - 1) // chunk
+        bytes_out = 0
+
+        def e2e_step():
+            nonlocal bytes_out
+            bank.reset()
+            bytes_out = 0
+            for k in range(nchunks):
+                r = bank.process_chunk(host_np[2 * k * chunk:2 * min((k + 1) * chunk, n_seg)])
+                bytes_out += r.audio.nbytes + r.clipped.nbytes
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        reps = max(1, min(steps, 3))
+        for _ in range(reps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": world * n_seg / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(4 * n_seg),
+               "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e2e_ms,
+               "api": "ChannelBank.process_chunk per 4 Mi-sample reference chunk, pinned host input"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_channelize) ---------------------------------------
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_in = seg_end - max(0, seg_begin - warm_rows * d)                 # samples one launch turns into channel rows
+    b_alg = 4.0 + sum(4.0 / d for _ in OFFSETS)                        # int16 in once + f32 audio out
+    chan_ms = timing["channelize_ms"] / max(timing["calls"], 1)
+    achieved = n_in * b_alg / (chan_ms * 1e-3) / 1e9 if chan_ms > 0 else None
+    traffic = None
+    prof = ROOT / "profiles" / "channelize_traffic.json"
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_sample", None)
+            traffic = traffic * n_in if traffic is not None else None
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_channelize<512,5,s16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "algorithmic_bytes_per_sample": b_alg, "kernel_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1),
+                "peak_source": peak_src}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_cpu = 2 * chunk
+        dt, _ = cpu_run(n_cpu, chunk, False)
+        cpu = {"value": n_cpu / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first 2 chunks ({n_cpu} samples), 5 targets sequential as cli.py:683 runs them; host has {os.cpu_count()} cores"}
+
+    value = world * n_seg / (step_ms * 1e-3) / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
+        "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
+                   "fft_size": bank.fft_size, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}",
+                   "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
+        "x_realtime": value * 1e6 / FS,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

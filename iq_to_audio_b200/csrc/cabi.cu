@@ -1,0 +1,887 @@
+// C ABI of libiq2a_b200.so (include/iq2a_b200.h): bank object, device memory, launch
+// sequencing.  Host-side logic only; all per-sample arithmetic lives in the kernels.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "stage.cuh"
+#include "tail.cuh"
+#include "../../include/iq2a_b200.h"
+
+namespace iq2a {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int frame_bytes(int codec) { return codec == CODEC_S16 ? 4 : codec == CODEC_U8 ? 2 : 8; }
+
+// Python's float modulo (processing.py:295 uses `%` on floats): result takes the divisor's sign.
+static inline double py_fmod(double a, double b) {
+    double r = std::fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return IQ2A_OK;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? IQ2A_ERR_NOMEM : IQ2A_ERR_CUDA;
+    }
+    return IQ2A_OK;
+}
+template <typename T>
+static int dev_grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return IQ2A_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 8 + 256;
+    int rc = dev_alloc(p, want);
+    if (rc != IQ2A_OK) return rc;
+    *cap = want;
+    return IQ2A_OK;
+}
+
+struct Group {
+    int first, count;
+    size_t g_off;     // offset (float2 elements) into d_gtab
+};
+
+}  // namespace iq2a
+
+using namespace iq2a;
+
+struct iq2a_bank {
+    iq2a_bank_config cfg{};
+    int C = 0, D = 1, M = 0, R1 = 32, vd = 0, ld = 0, n_sm = 148;
+    bool any_agc = false;
+    std::vector<std::vector<double>> taps;
+    std::vector<int> modes;
+    std::vector<double> w;          // signed NCO increments (sign * -2 pi f_off / fs)
+    std::vector<double> phase;      // streaming: NCO phase at n_pos per channel
+    std::vector<std::vector<double>> phase_tab;   // resident: per-chunk start phases (grown lazily)
+    std::vector<Group> groups;
+    int64_t n_pos = 0;              // streaming: input samples consumed
+    int64_t launches = 0;
+
+    float2* d_gtab = nullptr;
+    float2* d_tw = nullptr;
+    double* d_taps = nullptr;
+    int64_t* d_tap_off = nullptr;
+    int* d_ntaps = nullptr;
+    double* d_w = nullptr;
+    TailChan* d_chan = nullptr;
+    iq2a_channel_state* d_state = nullptr;
+    double* d_phase = nullptr;   size_t phase_cap = 0;
+    float2* d_bb = nullptr;      size_t bb_cap = 0;
+    float* d_pre = nullptr;      size_t pre_cap = 0;
+    float* d_tmp = nullptr;      size_t tmp_cap = 0;
+    float* d_audio = nullptr;    size_t audio_cap = 0;
+    float* d_clip = nullptr;     size_t clip_cap = 0;
+    double2* d_agg = nullptr;    size_t agg_cap = 0;
+    double* d_sumsq = nullptr;   size_t sumsq_cap = 0;
+    unsigned char* d_ring[2] = {nullptr, nullptr};
+    size_t ring_cap[2] = {0, 0};
+    int ring_cur = 0;
+    int64_t ring_frames = 0;        // frames currently held in d_ring[ring_cur] (all before n_pos)
+    cudaStream_t stream = nullptr;
+    // optional per-kernel timing (bench.py roofline): CUDA events on the launching stream
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before/after channel bank, after head, after tail
+    double t_chan_ms = 0, t_head_ms = 0, t_tail_ms = 0;
+    int64_t t_calls = 0;
+    bool ev_pending = false;
+
+    ~iq2a_bank() {
+        cudaSetDevice(cfg.device);
+        void* ptrs[] = {d_gtab, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+                        d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
+        for (void* q : ptrs)
+            if (q) cudaFree(q);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace iq2a {
+
+static int fresh_state(iq2a_bank* b) {
+    std::vector<iq2a_channel_state> st(b->C);
+    for (auto& s : st) {
+        std::memset(&s, 0, sizeof(s));
+        s.prev_re = 1.0f;   // decoders/nfm.py:15
+    }
+    IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_state, st.data(), st.size() * sizeof(st[0]), cudaMemcpyHostToDevice, b->stream));
+    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return IQ2A_OK;
+}
+
+// the reference's per-chunk phase bookkeeping (processing.py:295), extended lazily
+static void extend_phase_table(iq2a_bank* b, int64_t nchunks) {
+    const double two_pi = 2.0 * M_PI;
+    for (int c = 0; c < b->C; ++c) {
+        auto& t = b->phase_tab[c];
+        if (t.empty()) t.push_back(0.0);
+        while ((int64_t)t.size() < nchunks) {
+            const double step = b->w[c] * (double)b->cfg.ref_chunk;   // sign*increment*size
+            t.push_back(py_fmod(t.back() + step, two_pi));
+        }
+    }
+}
+
+struct CoreArgs {
+    const void* d_raw;
+    int64_t raw_n0, raw_len;
+    int64_t mg_begin, mg_emit, mg_end;   // rows [mg_begin, mg_end) computed, [mg_emit, mg_end) emitted
+    bool fresh;
+    // phase / segmentation model
+    int64_t seg_origin, seg_len;
+    int nseg;
+    const double* h_phase;               // host [C][nseg]
+    int64_t win0, nwin;                  // statistics windows (0 -> none)
+    float* d_audio;
+    float* d_clip;
+    float* d_bb_out;
+    int64_t out_stride;
+    cudaStream_t st;
+};
+
+static int run_core(iq2a_bank* b, const CoreArgs& a) {
+    const int C = b->C;
+    const int64_t n_rows = a.mg_end - a.mg_begin;
+    if (n_rows <= 0) return IQ2A_OK;
+    const int64_t stride = (n_rows + 63) & ~(int64_t)63;
+    int rc;
+    if ((rc = dev_grow(&b->d_bb, &b->bb_cap, (size_t)C * stride))) return rc;
+    if ((rc = dev_grow(&b->d_pre, &b->pre_cap, (size_t)C * stride))) return rc;
+    if (b->any_agc && (rc = dev_grow(&b->d_tmp, &b->tmp_cap, (size_t)C * stride))) return rc;
+    const int64_t ntiles = tail_tiles(n_rows);
+    if ((rc = dev_grow(&b->d_agg, &b->agg_cap, (size_t)C * ntiles))) return rc;
+    if ((rc = dev_grow(&b->d_phase, &b->phase_cap, (size_t)C * a.nseg))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_phase, a.h_phase, (size_t)C * a.nseg * sizeof(double),
+                                  cudaMemcpyHostToDevice, a.st));
+    if (a.nwin > 0) {
+        if ((rc = dev_grow(&b->d_sumsq, &b->sumsq_cap, (size_t)C * a.nwin))) return rc;
+        IQ2A_CUDA_TRY(cudaMemsetAsync(b->d_sumsq, 0, (size_t)C * a.nwin * sizeof(double), a.st));
+    }
+
+    const int order = b->cfg.iq_order;
+    const int swap = (order == IQ2A_ORDER_QI || order == IQ2A_ORDER_QI_INV);
+    const int neg = (order == IQ2A_ORDER_IQ_INV || order == IQ2A_ORDER_QI_INV);
+
+    if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[0], a.st));
+    // ---- channel bank: one launch per channel group -------------------------------------
+    for (const Group& g : b->groups) {
+        ChannelizeParams p{};
+        p.raw = a.d_raw;
+        p.raw_n0 = a.raw_n0;
+        p.raw_len = a.raw_len;
+        p.iq_swap = swap;
+        p.q_neg = neg;
+        p.decim = b->D;
+        p.vd = b->vd;
+        p.ld = b->ld;
+        p.mg_begin = a.mg_begin;
+        p.mg_end = a.mg_end;
+        p.nblocks = (int)ceil_div(n_rows, b->ld);
+        p.nchan = g.count;
+        p.gtab = b->d_gtab + g.g_off;
+        p.twid = b->d_tw;
+        p.out = b->d_bb + (size_t)g.first * stride;
+        p.out_stride = stride;
+        p.phase.tab = b->d_phase + (size_t)g.first * a.nseg;
+        p.phase.seg_len = a.seg_len;
+        p.phase.seg0_n = a.seg_origin;
+        p.phase.nseg = a.nseg;
+        for (int i = 0; i < g.count; ++i) p.w[i] = b->w[g.first + i];
+        if ((rc = launch_channelize(p, b->M, g.count, b->cfg.codec, b->n_sm, a.st))) return rc;
+        b->launches++;
+    }
+    if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[1], a.st));
+    // ---- head fix-up: stream start rows recomputed in float64 ----------------------------
+    if (a.mg_begin < b->vd) {
+        const int64_t last = std::min<int64_t>(a.mg_end, b->vd);
+        HeadParams h{};
+        h.raw = a.d_raw;
+        h.raw_n0 = a.raw_n0;
+        h.raw_len = a.raw_len;
+        h.iq_swap = swap;
+        h.q_neg = neg;
+        h.decim = b->D;
+        h.mg_begin = a.mg_begin;
+        h.taps = b->d_taps;
+        h.tap_offset = b->d_tap_off;
+        h.ntaps = b->d_ntaps;
+        h.w = b->d_w;
+        h.phase.tab = b->d_phase;
+        h.phase.seg_len = a.seg_len;
+        h.phase.seg0_n = a.seg_origin;
+        h.phase.nseg = a.nseg;
+        h.out = b->d_bb;
+        h.out_stride = stride;
+        h.out_mg0 = a.mg_begin;
+        if ((rc = launch_head_direct(h, b->cfg.codec, (int)(last - a.mg_begin), C, a.st))) return rc;
+        b->launches++;
+    }
+    if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[2], a.st));
+    // ---- channel-rate tail ------------------------------------------------------------------
+    TailParams t{};
+    t.bb = b->d_bb;
+    t.bb_stride = stride;
+    t.pre = b->d_pre;
+    t.tmp = b->d_tmp;
+    t.work_stride = stride;
+    t.audio = a.d_audio;
+    t.clipped = a.d_clip;
+    t.out_stride = a.out_stride;
+    t.agg = b->d_agg;
+    t.ntiles = ntiles;
+    t.sumsq = a.nwin > 0 ? b->d_sumsq : nullptr;
+    t.nwin = a.nwin;
+    t.win0 = a.win0;
+    t.state = b->d_state;
+    t.chan = b->d_chan;
+    t.nchan = C;
+    t.n = n_rows;
+    t.n_skip = a.mg_emit - a.mg_begin;
+    t.mg0 = a.mg_begin;
+    t.decim = b->D;
+    t.seg_origin = a.seg_origin;
+    t.seg_len = a.seg_len;
+    t.fresh = a.fresh ? 1 : 0;
+    t.dc_radius = 0.995;                          // decoders/common.py:9
+    t.agc_target = std::pow(10.0, -12.0 / 20.0);  // decoders/ssb.py:21,33
+    t.agc_decay = 0.001;                          // decoders/ssb.py:22
+    if ((rc = launch_tail(t, b->any_agc, a.st, &b->launches))) return rc;
+    if (b->timing) {
+        IQ2A_CUDA_TRY(cudaEventRecord(b->ev[3], a.st));
+        b->ev_pending = true;
+    }
+
+    if (a.d_bb_out) {
+        const int64_t n_emit = a.mg_end - a.mg_emit;
+        IQ2A_CUDA_TRY(cudaMemcpy2DAsync(a.d_bb_out, (size_t)a.out_stride * sizeof(float2),
+                                        b->d_bb + (a.mg_emit - a.mg_begin), (size_t)stride * sizeof(float2),
+                                        (size_t)n_emit * sizeof(float2), C, cudaMemcpyDeviceToDevice, a.st));
+    }
+    return IQ2A_OK;
+}
+
+// fold the last recorded events into the running totals (call after the stream is idle)
+static void collect_timing(iq2a_bank* b) {
+    if (!b->timing || !b->ev_pending) return;
+    float c = 0, h = 0, t = 0;
+    if (cudaEventElapsedTime(&c, b->ev[0], b->ev[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&h, b->ev[1], b->ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&t, b->ev[2], b->ev[3]) == cudaSuccess) {
+        b->t_chan_ms += c;
+        b->t_head_ms += h;
+        b->t_tail_ms += t;
+        b->t_calls++;
+    }
+    b->ev_pending = false;
+}
+
+static void stats_to_dbfs(const double* sumsq, const int64_t* counts, int64_t n, double* out) {
+    // decoders/nfm.py:87-88: rms = sqrt(mean(x^2) + 1e-18); dbfs = 20 log10(rms + 1e-12)
+    for (int64_t i = 0; i < n; ++i) {
+        const double mean = counts[i] > 0 ? sumsq[i] / (double)counts[i] : 0.0;
+        out[i] = 20.0 * std::log10(std::sqrt(mean + 1e-18) + 1e-12);
+    }
+}
+
+}  // namespace iq2a
+
+// =========================================================================================
+// extern "C"
+// =========================================================================================
+extern "C" {
+
+const char* iq2a_last_error(void) { return g_err; }
+int iq2a_version(void) { return 100; }
+
+int iq2a_device_count(int32_t* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device: %s", cudaGetErrorString(e));
+        if (count) *count = 0;
+        return IQ2A_ERR_STATE;
+    }
+    if (count) *count = n;
+    return IQ2A_OK;
+}
+
+int iq2a_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) { set_error("bad host_alloc arguments"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return IQ2A_OK;
+}
+int iq2a_host_free(void* ptr) {
+    if (ptr) IQ2A_CUDA_TRY(cudaFreeHost(ptr));
+    return IQ2A_OK;
+}
+
+int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, iq2a_bank** out) {
+    if (!cfg || !ch || !out) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->n_channels < 1 || cfg->n_channels > IQ2A_MAX_CHANNELS) { set_error("n_channels must be in [1, %d]", IQ2A_MAX_CHANNELS); return IQ2A_ERR_INVALID; }
+    if (!(cfg->sample_rate > 0)) { set_error("sample_rate must be positive"); return IQ2A_ERR_INVALID; }
+    if (cfg->decimation < 1) { set_error("decimation must be >= 1"); return IQ2A_ERR_INVALID; }
+    if (cfg->ref_chunk < 1) { set_error("ref_chunk must be >= 1"); return IQ2A_ERR_INVALID; }
+    if (cfg->codec < 0 || cfg->codec > 2) { set_error("unknown codec %d", cfg->codec); return IQ2A_ERR_INVALID; }
+    if (cfg->iq_order < 0 || cfg->iq_order > 3) { set_error("Unsupported iq_order %d", cfg->iq_order); return IQ2A_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (the B200 path has no CPU fallback)"); return IQ2A_ERR_STATE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range", cfg->device); return IQ2A_ERR_INVALID; }
+    int nt_max = 0;
+    for (int c = 0; c < cfg->n_channels; ++c) {
+        if (!ch[c].taps || ch[c].ntaps < 1) { set_error("channel %d: taps missing", c); return IQ2A_ERR_INVALID; }
+        if (ch[c].mix_sign != 1 && ch[c].mix_sign != -1) { set_error("channel %d: mix_sign must be +1 or -1", c); return IQ2A_ERR_INVALID; }
+        if (ch[c].mode < 0 || ch[c].mode > IQ2A_MODE_IQ) { set_error("channel %d: Unsupported demod mode %d", c, ch[c].mode); return IQ2A_ERR_INVALID; }
+        nt_max = std::max(nt_max, ch[c].ntaps);
+    }
+    const int D = cfg->decimation;
+    const int vd = (nt_max - 1 + D - 1) / D + 1;      // plan.py: overlap_rows
+    int M = cfg->fft_size;
+    if (M == 0) {
+        // cost per new sample ~ (5 log2 M + 8 C') / (1 - vd/M); 1024 only when it clearly wins
+        const double cm = std::min(cfg->n_channels, 6);
+        auto cost = [&](int m) { return m <= vd + 16 ? 1e300 : (5.0 * std::log2((double)m) + 8.0 * cm) / (1.0 - (double)vd / m); };
+        M = (cost(1024) < 0.95 * cost(512)) ? 1024 : 512;
+        if (cost(M) >= 1e300) { set_error("channel filter too long for the supported transform sizes (%d history rows)", vd); return IQ2A_ERR_INVALID; }
+    }
+    if (M != 512 && M != 1024) { set_error("fft_size must be 512 or 1024"); return IQ2A_ERR_INVALID; }
+    if (vd + 16 >= M) { set_error("channel filter too long for fft_size %d (%d history rows)", M, vd); return IQ2A_ERR_INVALID; }
+
+    iq2a_bank* b = new (std::nothrow) iq2a_bank();
+    if (!b) { set_error("out of host memory"); return IQ2A_ERR_NOMEM; }
+    b->cfg = *cfg;
+    b->C = cfg->n_channels;
+    b->D = D;
+    b->M = M;
+    b->R1 = 32;
+    b->vd = vd;
+    b->ld = M - vd;
+    int rc = IQ2A_OK;
+    auto fail = [&](int code) { delete b; return code; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", cfg->device); return fail(IQ2A_ERR_CUDA); }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(IQ2A_ERR_CUDA); }
+    b->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(IQ2A_ERR_CUDA); }
+
+    const int C = b->C;
+    b->taps.resize(C);
+    b->modes.resize(C);
+    b->w.resize(C);
+    b->phase.assign(C, 0.0);
+    b->phase_tab.assign(C, {});
+    std::vector<TailChan> tc(C);
+    std::vector<int64_t> toff(C);
+    std::vector<int> tn(C);
+    std::vector<double> all_taps;
+    for (int c = 0; c < C; ++c) {
+        b->taps[c].assign(ch[c].taps, ch[c].taps + ch[c].ntaps);
+        b->modes[c] = ch[c].mode;
+        // processing.py:287 and :293 -- increment = -2*pi*f/fs ; the ramp uses sign*increment
+        const double inc = -2.0 * M_PI * ch[c].freq_offset_hz / cfg->sample_rate;
+        b->w[c] = (double)ch[c].mix_sign * inc;
+        tc[c].mode = ch[c].mode;
+        tc[c].agc = ch[c].agc_enabled ? 1 : 0;
+        // decoders/nfm.py:40-47
+        const double fs_ch = cfg->sample_rate / D;
+        const double tau = std::max(ch[c].deemph_us * 1e-6, 1e-6);
+        tc[c].alpha = std::exp(-1.0 / (fs_ch * tau));
+        tc[c].beta = 1.0 - tc[c].alpha;
+        if ((ch[c].mode == IQ2A_MODE_USB || ch[c].mode == IQ2A_MODE_LSB) && ch[c].agc_enabled) b->any_agc = true;
+        toff[c] = (int64_t)all_taps.size();
+        tn[c] = ch[c].ntaps;
+        all_taps.insert(all_taps.end(), b->taps[c].begin(), b->taps[c].end());
+    }
+    // channel groups
+    const int gmax = channelize_max_group(M);
+    const int ng = (C + gmax - 1) / gmax;
+    size_t g_total = 0;
+    for (int g = 0, first = 0; g < ng; ++g) {
+        const int count = C / ng + (g < C % ng ? 1 : 0);
+        b->groups.push_back(Group{first, count, g_total});
+        g_total += (size_t)D * count * M;
+        first += count;
+    }
+    // device tables
+    std::vector<double2> wtab(M);
+    std::vector<float2> twf(M);
+    for (int t = 0; t < M; ++t) {
+        const double ang = -2.0 * M_PI * (double)t / (double)M;
+        wtab[t] = make_double2(std::cos(ang), std::sin(ang));
+        twf[t] = make_float2((float)wtab[t].x, (float)wtab[t].y);
+    }
+    double2* d_wtab = nullptr;
+    if ((rc = dev_alloc(&b->d_gtab, g_total)) || (rc = dev_alloc(&b->d_tw, (size_t)M)) ||
+        (rc = dev_alloc(&b->d_taps, all_taps.size())) || (rc = dev_alloc(&b->d_tap_off, (size_t)C)) ||
+        (rc = dev_alloc(&b->d_ntaps, (size_t)C)) || (rc = dev_alloc(&b->d_w, (size_t)C)) ||
+        (rc = dev_alloc(&b->d_chan, (size_t)C)) || (rc = dev_alloc(&b->d_state, (size_t)C)) ||
+        (rc = dev_alloc(&d_wtab, (size_t)M)))
+        return fail(rc);
+    bool ok = true;
+    ok &= cudaMemcpy(b->d_tw, twf.data(), M * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(d_wtab, wtab.data(), M * sizeof(double2), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(b->d_taps, all_taps.data(), all_taps.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(b->d_tap_off, toff.data(), C * sizeof(int64_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(b->d_ntaps, tn.data(), C * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(b->d_w, b->w.data(), C * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(b->d_chan, tc.data(), C * sizeof(TailChan), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { cudaFree(d_wtab); set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(IQ2A_ERR_CUDA); }
+    for (const Group& g : b->groups)
+        for (int i = 0; i < g.count; ++i) {
+            const int c = g.first + i;
+            rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
+                                b->d_gtab + g.g_off, g.count, i, b->stream);
+            if (rc) { cudaFree(d_wtab); return fail(rc); }
+            b->launches++;
+        }
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    cudaFree(d_wtab);
+    if (e != cudaSuccess) { set_error("G-table build failed: %s", cudaGetErrorString(e)); return fail(IQ2A_ERR_CUDA); }
+    if ((rc = fresh_state(b))) return fail(rc);
+    *out = b;
+    return IQ2A_OK;
+}
+
+void iq2a_bank_destroy(iq2a_bank* bank) { delete bank; }
+
+int iq2a_bank_info_get(const iq2a_bank* b, iq2a_bank_info* info) {
+    if (!b || !info) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    info->fft_size = b->M;
+    info->overlap_rows = b->vd;
+    info->rows_per_block = b->ld;
+    info->n_channels = b->C;
+    info->hop = (int64_t)b->ld * b->D;
+    info->halo = (int64_t)b->vd * b->D;
+    info->fs_channel = b->cfg.sample_rate / b->D;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_reset(iq2a_bank* b) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    b->n_pos = 0;
+    b->ring_frames = 0;
+    std::fill(b->phase.begin(), b->phase.end(), 0.0);
+    return fresh_state(b);
+}
+
+int iq2a_bank_get_state(const iq2a_bank* b, iq2a_channel_state* states, int64_t* consumed) {
+    if (!b || !states) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    IQ2A_CUDA_TRY(cudaMemcpy(states, b->d_state, b->C * sizeof(iq2a_channel_state), cudaMemcpyDeviceToHost));
+    if (consumed) *consumed = b->n_pos;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_set_state(iq2a_bank* b, const iq2a_channel_state* states) {
+    if (!b || !states) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    IQ2A_CUDA_TRY(cudaMemcpy(b->d_state, states, b->C * sizeof(iq2a_channel_state), cudaMemcpyHostToDevice));
+    return IQ2A_OK;
+}
+
+int iq2a_bank_launch_count(const iq2a_bank* b, int64_t* launches) {
+    if (!b || !launches) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    *launches = b->launches;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_set_timing(iq2a_bank* b, int32_t enable) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    if (enable && !b->ev[0])
+        for (auto& e : b->ev) IQ2A_CUDA_TRY(cudaEventCreate(&e));
+    b->timing = enable != 0;
+    b->t_chan_ms = b->t_head_ms = b->t_tail_ms = 0;
+    b->t_calls = 0;
+    b->ev_pending = false;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_get_timing(iq2a_bank* b, double* channelize_ms, double* head_ms, double* tail_ms, int64_t* calls) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (b->ev_pending) {
+        IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+        IQ2A_CUDA_TRY(cudaEventSynchronize(b->ev[3]));
+        collect_timing(b);
+    }
+    if (channelize_ms) *channelize_ms = b->t_chan_ms;
+    if (head_ms) *head_ms = b->t_head_ms;
+    if (tail_ms) *tail_ms = b->t_tail_ms;
+    if (calls) *calls = b->t_calls;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_copy_gtable(const iq2a_bank* b, float* host_out, int64_t n_complex) {
+    if (!b || !host_out) { set_error("null argument"); return IQ2A_ERR_INVALID; }
+    const size_t per = (size_t)b->D * b->M;
+    if ((size_t)n_complex < per * b->C) { set_error("gtable buffer too small"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    // device layout is [group][D][cg][M]; hand back [C][D][M]
+    std::vector<float2> tmp;
+    for (const Group& g : b->groups) {
+        tmp.resize(per * g.count);
+        IQ2A_CUDA_TRY(cudaMemcpy(tmp.data(), b->d_gtab + g.g_off, tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < g.count; ++i)
+            for (int p = 0; p < b->D; ++p)
+                std::memcpy(host_out + 2 * (((size_t)(g.first + i) * b->D + p) * b->M),
+                            tmp.data() + ((size_t)p * g.count + i) * b->M, b->M * sizeof(float2));
+    }
+    return IQ2A_OK;
+}
+
+int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, float* audio, float* clipped,
+                            float* baseband, int64_t out_stride, int64_t* n_out, double* rms_dbfs) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (n_frames < 0 || (n_frames > 0 && !frames)) { set_error("bad frame buffer"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    const int C = b->C, D = b->D;
+    const int fb = frame_bytes(b->cfg.codec);
+    const int64_t mg_begin = ceil_div(b->n_pos, D);
+    const int64_t mg_end = ceil_div(b->n_pos + n_frames, D);
+    const int64_t rows = mg_end - mg_begin;
+    if (n_out) *n_out = rows;
+    if (n_frames == 0) return IQ2A_OK;                 // every stage returns its (empty) input
+    if (rows > out_stride && (audio || clipped || baseband)) { set_error("output stride %lld < %lld rows", (long long)out_stride, (long long)rows); return IQ2A_ERR_INVALID; }
+
+    // stream buffer: [history | new chunk]; history = the (vd+1)*D frames before n_pos
+    const int64_t want_hist = std::min<int64_t>((int64_t)(b->vd + 1) * D, b->n_pos);
+    const int64_t keep = std::min(want_hist, b->ring_frames);
+    const int nxt = b->ring_cur ^ 1;
+    int rc = dev_grow(&b->d_ring[nxt], &b->ring_cap[nxt], (size_t)(keep + n_frames) * fb + 16);
+    if (rc) return rc;
+    if (keep > 0)
+        IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_ring[nxt], b->d_ring[b->ring_cur] + (size_t)(b->ring_frames - keep) * fb,
+                                      (size_t)keep * fb, cudaMemcpyDeviceToDevice, b->stream));
+    IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_ring[nxt] + (size_t)keep * fb, frames, (size_t)n_frames * fb,
+                                  cudaMemcpyHostToDevice, b->stream));
+    b->ring_cur = nxt;
+    b->ring_frames = keep + n_frames;
+
+    if ((rc = dev_grow(&b->d_audio, &b->audio_cap, (size_t)C * std::max<int64_t>(rows, 1)))) return rc;
+    if ((rc = dev_grow(&b->d_clip, &b->clip_cap, (size_t)C * std::max<int64_t>(rows, 1)))) return rc;
+
+    CoreArgs a{};
+    a.d_raw = b->d_ring[nxt];
+    a.raw_n0 = b->n_pos - keep;
+    a.raw_len = keep + n_frames;
+    a.mg_begin = a.mg_emit = mg_begin;
+    a.mg_end = mg_end;
+    a.fresh = false;
+    a.seg_origin = b->n_pos;          // one call == one reference chunk
+    a.seg_len = std::max<int64_t>(n_frames, 1);
+    a.nseg = 1;
+    a.h_phase = b->phase.data();
+    a.win0 = 0;
+    a.nwin = rows > 0 ? 1 : 0;
+    a.d_audio = b->d_audio;
+    a.d_clip = b->d_clip;
+    a.d_bb_out = nullptr;
+    a.out_stride = std::max<int64_t>(rows, 1);
+    a.st = b->stream;
+    if (rows > 0 && (rc = run_core(b, a))) return rc;
+
+    // the reference's phase carry (processing.py:295), and the sample counter
+    for (int c = 0; c < C; ++c) b->phase[c] = py_fmod(b->phase[c] + b->w[c] * (double)n_frames, 2.0 * M_PI);
+    b->n_pos += n_frames;
+
+    if (rows > 0) {
+        if (audio)
+            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(audio, out_stride * sizeof(float), b->d_audio, rows * sizeof(float),
+                                            rows * sizeof(float), C, cudaMemcpyDeviceToHost, b->stream));
+        if (clipped)
+            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(clipped, out_stride * sizeof(float), b->d_clip, rows * sizeof(float),
+                                            rows * sizeof(float), C, cudaMemcpyDeviceToHost, b->stream));
+        if (baseband) {
+            const int64_t stride = (rows + 63) & ~(int64_t)63;
+            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(baseband, out_stride * sizeof(float2), b->d_bb, stride * sizeof(float2),
+                                            rows * sizeof(float2), C, cudaMemcpyDeviceToHost, b->stream));
+        }
+    }
+    std::vector<double> ss(C, 0.0);
+    if (rms_dbfs && rows > 0)
+        IQ2A_CUDA_TRY(cudaMemcpyAsync(ss.data(), b->d_sumsq, C * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    collect_timing(b);
+    if (rms_dbfs) {
+        std::vector<int64_t> cnt(C, rows);
+        stats_to_dbfs(ss.data(), cnt.data(), C, rms_dbfs);
+    }
+    return IQ2A_OK;
+}
+
+static int resident_common(iq2a_bank* b, const void* dev_frames, int64_t first_frame, int64_t n_frames,
+                           int64_t seg_begin, int64_t seg_end, int32_t warmup_rows, float* dev_audio,
+                           float* dev_clipped, float* dev_baseband, int64_t out_stride, cudaStream_t st,
+                           int64_t* n_out, int64_t* win0_out, int64_t* nwin_out, int64_t* mg_emit_out) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (!dev_frames || n_frames <= 0) { set_error("no frames"); return IQ2A_ERR_INVALID; }
+    if (seg_begin < 0 || seg_end < seg_begin || warmup_rows < 0) { set_error("bad segment [%lld, %lld)", (long long)seg_begin, (long long)seg_end); return IQ2A_ERR_INVALID; }
+    if (seg_end > first_frame + n_frames) { set_error("segment end %lld beyond the resident frames", (long long)seg_end); return IQ2A_ERR_INVALID; }
+    const int D = b->D;
+    const int64_t mg_emit = ceil_div(seg_begin, D);
+    const int64_t mg_end = ceil_div(seg_end, D);
+    const int64_t mg_begin = std::max<int64_t>(0, mg_emit - warmup_rows);
+    // history the first computed row needs
+    const int64_t need_from = std::max<int64_t>(0, (mg_begin - b->vd) * (int64_t)D);
+    if (first_frame > need_from) {
+        set_error("segment needs input history from sample %lld but the resident frames start at %lld",
+                  (long long)need_from, (long long)first_frame);
+        return IQ2A_ERR_INVALID;
+    }
+    if (n_out) *n_out = mg_end - mg_emit;
+    if (mg_end - mg_emit > out_stride && (dev_audio || dev_clipped || dev_baseband)) { set_error("output stride too small"); return IQ2A_ERR_INVALID; }
+    const int64_t chunk = b->cfg.ref_chunk;
+    const int64_t k_lo = need_from / chunk;
+    const int64_t k_hi = (std::max<int64_t>(seg_end, 1) - 1) / chunk;
+    extend_phase_table(b, k_hi + 1);
+    const int nseg = (int)(k_hi - k_lo + 1);
+    std::vector<double> hp((size_t)b->C * nseg);
+    for (int c = 0; c < b->C; ++c)
+        for (int k = 0; k < nseg; ++k) hp[(size_t)c * nseg + k] = b->phase_tab[c][k_lo + k];
+
+    CoreArgs a{};
+    a.d_raw = dev_frames;
+    a.raw_n0 = first_frame;
+    a.raw_len = n_frames;
+    a.mg_begin = mg_begin;
+    a.mg_emit = mg_emit;
+    a.mg_end = mg_end;
+    a.fresh = (warmup_rows > 0) || (seg_begin == 0);
+    a.seg_origin = k_lo * chunk;
+    a.seg_len = chunk;
+    a.nseg = nseg;
+    a.h_phase = hp.data();
+    a.win0 = seg_begin / chunk - k_lo;
+    a.nwin = k_hi - seg_begin / chunk + 1;
+    a.d_audio = dev_audio;
+    a.d_clip = dev_clipped;
+    a.d_bb_out = dev_baseband;
+    a.out_stride = out_stride;
+    a.st = st;
+    if (win0_out) *win0_out = seg_begin / chunk;
+    if (nwin_out) *nwin_out = a.nwin;
+    if (mg_emit_out) *mg_emit_out = mg_emit;
+    // hp must outlive the async H2D copy: run_core copies from pageable memory, which the
+    // runtime stages before returning, so the vector may go out of scope afterwards.
+    return run_core(b, a);
+}
+
+int iq2a_bank_process_resident(iq2a_bank* b, const void* dev_frames, int64_t first_frame, int64_t n_frames,
+                               int64_t seg_begin, int64_t seg_end, int32_t warmup_rows, float* dev_audio,
+                               float* dev_clipped, float* dev_baseband, int64_t out_stride, int64_t* n_out,
+                               double* rms_dbfs, int64_t rms_capacity) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    int64_t win0 = 0, nwin = 0, mg_emit = 0;
+    int rc = resident_common(b, dev_frames, first_frame, n_frames, seg_begin, seg_end, warmup_rows, dev_audio,
+                             dev_clipped, dev_baseband, out_stride, b->stream, n_out, &win0, &nwin, &mg_emit);
+    if (rc) return rc;
+    if (rms_dbfs && nwin > 0) {
+        if (rms_capacity < nwin) { set_error("rms buffer holds %lld windows, need %lld", (long long)rms_capacity, (long long)nwin); return IQ2A_ERR_INVALID; }
+        std::vector<double> ss((size_t)b->C * nwin);
+        IQ2A_CUDA_TRY(cudaMemcpyAsync(ss.data(), b->d_sumsq, ss.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+        const int64_t chunk = b->cfg.ref_chunk;
+        const int D = b->D;
+        std::vector<int64_t> cnt(nwin);
+        for (int64_t k = 0; k < nwin; ++k) {
+            const int64_t lo = std::max((win0 + k) * chunk, seg_begin), hi = std::min((win0 + k + 1) * chunk, seg_end);
+            cnt[k] = hi > lo ? ceil_div(hi, D) - ceil_div(lo, D) : 0;
+        }
+        for (int c = 0; c < b->C; ++c) stats_to_dbfs(ss.data() + (size_t)c * nwin, cnt.data(), nwin, rms_dbfs + (size_t)c * rms_capacity);
+    }
+    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    collect_timing(b);
+    return IQ2A_OK;
+}
+
+int iq2a_bank_process_resident_async(iq2a_bank* b, const void* dev_frames, int64_t first_frame, int64_t n_frames,
+                                     int64_t seg_begin, int64_t seg_end, int32_t warmup_rows, float* dev_audio,
+                                     float* dev_clipped, float* dev_baseband, int64_t out_stride, void* cuda_stream) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    return resident_common(b, dev_frames, first_frame, n_frames, seg_begin, seg_end, warmup_rows, dev_audio,
+                           dev_clipped, dev_baseband, out_stride, (cudaStream_t)cuda_stream, nullptr, nullptr,
+                           nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage-level entry points (host arrays in, host arrays out)
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return IQ2A_ERR_NOMEM; }
+        return IQ2A_OK;
+    }
+};
+
+static int stage_device(int32_t device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (the B200 path has no CPU fallback)"); return IQ2A_ERR_STATE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaSetDevice(device));
+    return IQ2A_OK;
+}
+
+int iq2a_unpack_mix(const void* frames, int64_t n_frames, int32_t codec, int32_t iq_order, double phase,
+                    double w_signed, float* out_c64, int32_t device) {
+    if (n_frames < 0 || (n_frames && (!frames || !out_c64))) { set_error("bad arguments"); return IQ2A_ERR_INVALID; }
+    if (codec < 0 || codec > 2) { set_error("unknown codec %d", codec); return IQ2A_ERR_INVALID; }
+    if (iq_order < 0 || iq_order > 3) { set_error("Unsupported iq_order %d", iq_order); return IQ2A_ERR_INVALID; }
+    if (n_frames == 0) return IQ2A_OK;
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf in, out;
+    const size_t fb = frame_bytes(codec);
+    if ((rc = in.alloc(n_frames * fb)) || (rc = out.alloc(n_frames * sizeof(float2)))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(in.p, frames, n_frames * fb, cudaMemcpyHostToDevice));
+    if ((rc = launch_unpack_mix(in.p, n_frames, codec, iq_order, phase, w_signed, (float2*)out.p, 0))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(out_c64, out.p, n_frames * sizeof(float2), cudaMemcpyDeviceToHost));
+    return IQ2A_OK;
+}
+
+int iq2a_fir(const float* in_c64, int64_t n, const float* history_c64, const double* taps, int32_t ntaps,
+             float* out_c64, int32_t device) {
+    if (n < 0 || ntaps < 1 || !taps || (n && (!in_c64 || !out_c64))) { set_error("bad arguments"); return IQ2A_ERR_INVALID; }
+    if (n == 0) return IQ2A_OK;
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf x, y, h;
+    const int64_t nh = ntaps - 1;
+    if ((rc = x.alloc((n + nh) * sizeof(float2))) || (rc = y.alloc(n * sizeof(float2))) || (rc = h.alloc(ntaps * sizeof(double)))) return rc;
+    if (nh) {
+        if (history_c64) IQ2A_CUDA_TRY(cudaMemcpy(x.p, history_c64, nh * sizeof(float2), cudaMemcpyHostToDevice));
+        else IQ2A_CUDA_TRY(cudaMemset(x.p, 0, nh * sizeof(float2)));
+    }
+    IQ2A_CUDA_TRY(cudaMemcpy((float2*)x.p + nh, in_c64, n * sizeof(float2), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemcpy(h.p, taps, ntaps * sizeof(double), cudaMemcpyHostToDevice));
+    if ((rc = launch_fir_direct((const float2*)x.p, n, (const double*)h.p, ntaps, (float2*)y.p, 0))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(out_c64, y.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    return IQ2A_OK;
+}
+
+int iq2a_decimate(const float* in_c64, int64_t n, int32_t factor, int64_t offset, float* out_c64, int64_t* n_out,
+                  int32_t device) {
+    if (n < 0 || factor < 1 || offset < 0) { set_error("bad arguments"); return IQ2A_ERR_INVALID; }
+    const int64_t start = ((-offset) % factor + factor) % factor;     // processing.py:357
+    const int64_t cnt = n > start ? ceil_div(n - start, factor) : 0;
+    if (n_out) *n_out = cnt;
+    if (cnt == 0) return IQ2A_OK;
+    if (!in_c64 || !out_c64) { set_error("null buffers"); return IQ2A_ERR_INVALID; }
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf x, y;
+    if ((rc = x.alloc(n * sizeof(float2))) || (rc = y.alloc(cnt * sizeof(float2)))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(x.p, in_c64, n * sizeof(float2), cudaMemcpyHostToDevice));
+    if ((rc = launch_decimate((const float2*)x.p, start, factor, cnt, (float2*)y.p, 0))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(out_c64, y.p, cnt * sizeof(float2), cudaMemcpyDeviceToHost));
+    return IQ2A_OK;
+}
+
+int iq2a_demod(int32_t mode, int32_t agc_enabled, double deemph_alpha, const float* in_c64, int64_t n,
+               iq2a_channel_state* state, float* audio, double* rms_dbfs, int32_t device) {
+    if (mode < 0 || mode > IQ2A_MODE_LSB) { set_error("Unsupported demod mode %d", mode); return IQ2A_ERR_INVALID; }
+    if (n < 0 || !state || (n && (!in_c64 || !audio))) { set_error("bad arguments"); return IQ2A_ERR_INVALID; }
+    if (n == 0) return IQ2A_OK;
+    int rc = stage_device(device);
+    if (rc) return rc;
+    const int64_t stride = (n + 63) & ~(int64_t)63;
+    const int64_t ntiles = tail_tiles(n);
+    DevBuf bb, pre, tmp, aud, agg, ss, st, chn;
+    if ((rc = bb.alloc(stride * sizeof(float2))) || (rc = pre.alloc(stride * sizeof(float))) ||
+        (rc = tmp.alloc(stride * sizeof(float))) || (rc = aud.alloc(stride * sizeof(float))) ||
+        (rc = agg.alloc(ntiles * sizeof(double2))) || (rc = ss.alloc(sizeof(double))) ||
+        (rc = st.alloc(sizeof(iq2a_channel_state))) || (rc = chn.alloc(sizeof(TailChan))))
+        return rc;
+    TailChan tc{mode, agc_enabled ? 1 : 0, deemph_alpha, 1.0 - deemph_alpha};
+    IQ2A_CUDA_TRY(cudaMemcpy(bb.p, in_c64, n * sizeof(float2), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemcpy(st.p, state, sizeof(*state), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemcpy(chn.p, &tc, sizeof(tc), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemset(ss.p, 0, sizeof(double)));
+    TailParams t{};
+    t.bb = (const float2*)bb.p;  t.bb_stride = stride;
+    t.pre = (float*)pre.p;       t.tmp = (float*)tmp.p;   t.work_stride = stride;
+    t.audio = (float*)aud.p;     t.clipped = nullptr;     t.out_stride = stride;
+    t.agg = (double2*)agg.p;     t.ntiles = ntiles;
+    t.sumsq = (double*)ss.p;     t.nwin = 1;              t.win0 = 0;
+    t.state = (iq2a_channel_state*)st.p;
+    t.chan = (const TailChan*)chn.p;
+    t.nchan = 1;
+    t.n = n;  t.n_skip = 0;  t.mg0 = 0;  t.decim = 1;
+    t.seg_origin = 0;  t.seg_len = std::max<int64_t>(n, 1);   // one call == one chunk: AGC restarts at row 0
+    t.fresh = 0;
+    t.dc_radius = 0.995;  t.agc_target = std::pow(10.0, -12.0 / 20.0);  t.agc_decay = 0.001;
+    const bool agc = (mode == IQ2A_MODE_USB || mode == IQ2A_MODE_LSB) && agc_enabled;
+    if ((rc = launch_tail(t, agc, 0, nullptr))) return rc;
+    double sumsq = 0.0;
+    IQ2A_CUDA_TRY(cudaMemcpy(audio, aud.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    IQ2A_CUDA_TRY(cudaMemcpy(state, st.p, sizeof(*state), cudaMemcpyDeviceToHost));
+    IQ2A_CUDA_TRY(cudaMemcpy(&sumsq, ss.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (rms_dbfs) stats_to_dbfs(&sumsq, &n, 1, rms_dbfs);
+    return IQ2A_OK;
+}
+
+int iq2a_scan(int32_t kind, double deemph_alpha, const float* in, int64_t n, iq2a_channel_state* state,
+              float* out, int32_t device) {
+    if (kind < 0 || kind > 2) { set_error("unknown recurrence kind %d", kind); return IQ2A_ERR_INVALID; }
+    if (n < 0 || !state || (n && (!in || !out))) { set_error("bad arguments"); return IQ2A_ERR_INVALID; }
+    if (n == 0) return IQ2A_OK;
+    int rc = stage_device(device);
+    if (rc) return rc;
+    const int64_t stride = (n + 63) & ~(int64_t)63;
+    const int64_t ntiles = tail_tiles(n);
+    DevBuf pre, aud, agg, st, chn;
+    if ((rc = pre.alloc(stride * sizeof(float))) || (rc = aud.alloc(stride * sizeof(float))) ||
+        (rc = agg.alloc(ntiles * sizeof(double2))) || (rc = st.alloc(sizeof(iq2a_channel_state))) ||
+        (rc = chn.alloc(sizeof(TailChan))))
+        return rc;
+    TailChan tc{MODE_RAW_DEEMPH + kind, 0, deemph_alpha, 1.0 - deemph_alpha};
+    IQ2A_CUDA_TRY(cudaMemcpy(pre.p, in, n * sizeof(float), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemcpy(st.p, state, sizeof(*state), cudaMemcpyHostToDevice));
+    IQ2A_CUDA_TRY(cudaMemcpy(chn.p, &tc, sizeof(tc), cudaMemcpyHostToDevice));
+    TailParams t{};
+    t.pre = (float*)pre.p;  t.tmp = nullptr;  t.work_stride = stride;
+    t.audio = (float*)aud.p;  t.out_stride = stride;
+    t.agg = (double2*)agg.p;  t.ntiles = ntiles;
+    t.state = (iq2a_channel_state*)st.p;
+    t.chan = (const TailChan*)chn.p;
+    t.nchan = 1;
+    t.n = n;  t.mg0 = 0;  t.decim = 1;
+    t.seg_origin = 0;  t.seg_len = std::max<int64_t>(n, 1);
+    t.skip_pre = 1;
+    t.dc_radius = 0.995;  t.agc_target = std::pow(10.0, -12.0 / 20.0);  t.agc_decay = 0.001;
+    const float peak_in = state->peak;
+    if ((rc = launch_tail(t, false, 0, nullptr))) return rc;
+    IQ2A_CUDA_TRY(cudaMemcpy(out, aud.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    IQ2A_CUDA_TRY(cudaMemcpy(state, st.p, sizeof(*state), cudaMemcpyDeviceToHost));
+    state->peak = peak_in;      // the peak belongs to the writer, not to a bare recurrence
+    return IQ2A_OK;
+}
+
+}  // extern "C"

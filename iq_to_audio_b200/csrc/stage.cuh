@@ -1,0 +1,34 @@
+// Launchers of the stage-level / setup kernels (stage.cu) and of the channel bank (channelizer.cu).
+#pragma once
+#include "common.cuh"
+
+namespace iq2a {
+
+struct HeadParams {
+    const void* raw;
+    int64_t raw_n0, raw_len;
+    int iq_swap, q_neg, decim;
+    int64_t mg_begin;          // first channel-rate row to recompute (global index)
+    const double* taps;        // all channels' taps, concatenated (device)
+    const int64_t* tap_offset; // [C] (device)
+    const int* ntaps;          // [C] (device)
+    const double* w;           // [C] signed NCO increments (device)
+    PhaseModel phase;          // tab rows indexed by global channel
+    float2* out;               // [C][out_stride]
+    int64_t out_stride;
+    int64_t out_mg0;           // decimated index of out[.][0]
+};
+
+int launch_unpack_mix(const void* d_raw, int64_t n, int codec, int iq_order, double phase, double w,
+                      float2* d_out, cudaStream_t st);
+int launch_fir_direct(const float2* d_x, int64_t n_out, const double* d_taps, int ntaps, float2* d_y,
+                      cudaStream_t st);
+int launch_decimate(const float2* d_x, int64_t start, int factor, int64_t n_out, float2* d_y, cudaStream_t st);
+int launch_head_direct(const HeadParams& p, int codec, int nrows, int nchan, cudaStream_t st);
+int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int R1, int qn,
+                   const double2* d_wtab, float2* d_gout, int cg, int c_in_group, cudaStream_t st);
+
+int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, int n_sm, cudaStream_t st);
+int channelize_max_group(int m_fft);
+
+}  // namespace iq2a

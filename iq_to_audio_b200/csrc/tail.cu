@@ -1,0 +1,294 @@
+// Channel-rate tail: discriminator / envelope / product detector, then the decoder
+// recurrences as parallel affine scans in float64, then the writer-side peak / clip and
+// the per-chunk statistics.
+//
+// Reference arithmetic replaced (src/iq_to_audio/decoders/):
+//   nfm.py:17-24   QuadratureDemod.process   angle(s[n] conj(s[n-1]))            -> k_pre
+//   am.py:28       abs(s)                                                        -> k_pre
+//   ssb.py:42-43   real(s) (USB) / real(conj s) (LSB)                            -> k_pre
+//   nfm.py:49-62   DeemphasisFilter: y = beta x + z ; z = alpha y (lfilter DF2T) -> scan DEEMPH
+//   common.py:16-30 DCBlocker: y = x - x1 + r y1                                 -> scan DC
+//   ssb.py:67-80   AGC: g += decay (target/|x| - g), g restarts at 1 per chunk   -> scan AGC
+//   processing.py:449-453 AudioWriter.write: running pre-clip peak, clip +-0.99  -> emit
+//   nfm.py:87-89   per-chunk RMS dBFS (sum of squares accumulated here)          -> emit
+//
+// Every recurrence is first-order and affine in its carried variable,
+//   v[m] = A_m v[m-1] + B_m,
+// so it composes associatively: (A2,B2) o (A1,B1) = (A2 A1, A2 B1 + B2).  Three kernels:
+// per-tile aggregate, a serial walk over tile aggregates (a few thousand steps per
+// channel), per-tile apply.  All in float64: the reference runs the de-emphasis in
+// float64 (lfilter) and the DC blocker / AGC as float32 sequential loops; float64 scans
+// differ from those by < 1e-5 pre-clip, well inside the 1e-4 tolerance.
+#include "common.cuh"
+#include "tail.cuh"
+#include "../../include/iq2a_b200.h"
+
+namespace iq2a {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 4;
+constexpr int kScanTile = kScanThreads * kScanPer;
+
+struct Aff {
+    double a, b;
+};
+__device__ __forceinline__ Aff compose(Aff first, Aff second) {   // second o first
+    return Aff{second.a * first.a, fma(second.a, first.b, second.b)};
+}
+
+__device__ __forceinline__ bool is_chunk_start(const TailParams& p, int64_t r) {
+    const int64_t n = (p.mg0 + r) * (int64_t)p.decim - p.seg_origin;
+    if (n < 0) return false;
+    return (n % p.seg_len) < p.decim;
+}
+
+// ---------------------------------------------------------------------------------------
+// detector front: complex64 channel samples -> float32 "pre-audio"
+// ---------------------------------------------------------------------------------------
+__global__ void k_pre(const TailParams p) {
+    const int c = blockIdx.y;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n) return;
+    const TailChan ch = p.chan[c];
+    const float2* bb = p.bb + (size_t)c * p.bb_stride;
+    const float2 s = bb[r];
+    float out;
+    if (ch.mode == MODE_NFM) {
+        float2 prev;
+        if (r > 0) prev = bb[r - 1];
+        else if (p.fresh) prev = make_float2(1.f, 0.f);          // nfm.py:15
+        else prev = make_float2(p.state[c].prev_re, p.state[c].prev_im);
+        // numpy complex64 product s * conj(prev), then arctan2 (nfm.py:21-22)
+        const float re = __fadd_rn(__fmul_rn(s.x, prev.x), __fmul_rn(s.y, prev.y));
+        const float im = __fsub_rn(__fmul_rn(s.y, prev.x), __fmul_rn(s.x, prev.y));
+        out = atan2f(im, re);
+    } else if (ch.mode == MODE_AM) {
+        out = hypotf(s.x, s.y);                                  // am.py:28
+    } else {
+        out = s.x;                                               // ssb.py:42-43
+    }
+    p.pre[(size_t)c * p.work_stride + r] = out;
+}
+
+// ---------------------------------------------------------------------------------------
+// scan element definitions
+// ---------------------------------------------------------------------------------------
+enum ScanKind : int { SCAN_NONE = -1, SCAN_DEEMPH = 0, SCAN_DC = 1, SCAN_AGC = 2 };
+
+__device__ __forceinline__ int scan_kind(const TailChan& ch, int pass) {
+    if (pass == 0) {
+        if (ch.mode == MODE_NFM || ch.mode == MODE_RAW_DEEMPH) return SCAN_DEEMPH;
+        if (ch.mode == MODE_AM || ch.mode == MODE_USB || ch.mode == MODE_LSB || ch.mode == MODE_RAW_DC) return SCAN_DC;
+        if (ch.mode == MODE_RAW_AGC) return SCAN_AGC;
+        return SCAN_NONE;
+    }
+    if ((ch.mode == MODE_USB || ch.mode == MODE_LSB) && ch.agc) return SCAN_AGC;
+    return SCAN_NONE;
+}
+__device__ __forceinline__ bool scan_is_final(const TailChan& ch, int pass, int kind) {
+    if (pass == 1) return true;
+    return !(kind == SCAN_DC && (ch.mode == MODE_USB || ch.mode == MODE_LSB) && ch.agc);
+}
+
+struct ScanCtx {
+    int kind;
+    const float* x;     // input row for this channel
+    double alpha, beta; // DEEMPH
+    double r;           // DC radius
+    float x_before;     // DC: x[-1]
+};
+
+__device__ __forceinline__ Aff scan_elem(const TailParams& p, const ScanCtx& k, int64_t r) {
+    if (k.kind == SCAN_DEEMPH) {
+        // z[m] = alpha*y[m] = alpha*z[m-1] + alpha*(beta*x[m])
+        return Aff{k.alpha, k.alpha * (k.beta * (double)k.x[r])};
+    }
+    if (k.kind == SCAN_DC) {
+        const float xm1 = r > 0 ? k.x[r - 1] : k.x_before;
+        return Aff{k.r, (double)__fsub_rn(k.x[r], xm1)};        // common.py:24 float32 difference
+    }
+    // AGC (ssb.py:74-78)
+    const float mag = fabsf(k.x[r]);
+    double a = 1.0, b = 0.0;
+    if (mag > 1e-6f) {
+        a = 1.0 - p.agc_decay;
+        b = p.agc_decay * (p.agc_target / (double)mag);
+    }
+    if (is_chunk_start(p, r)) return Aff{0.0, a + b};            // gain restarts at 1.0 (ssb.py:72)
+    return Aff{a, b};
+}
+
+__device__ __forceinline__ float scan_emit(const ScanCtx& k, int64_t r, double v_prev, double v_cur) {
+    if (k.kind == SCAN_DEEMPH) return (float)(k.beta * (double)k.x[r] + v_prev);   // y = b0 x + z
+    if (k.kind == SCAN_DC) return (float)v_cur;
+    return __fmul_rn(k.x[r], (float)v_cur);                                        // ssb.py:79
+}
+
+__device__ __forceinline__ ScanCtx make_ctx(const TailParams& p, int c, int pass, const TailChan& ch) {
+    ScanCtx k;
+    k.kind = scan_kind(ch, pass);
+    k.alpha = ch.alpha;
+    k.beta = ch.beta;
+    k.r = p.dc_radius;
+    k.x = (pass == 0 ? p.pre : p.tmp) + (size_t)c * p.work_stride;
+    k.x_before = p.fresh ? 0.f : p.state[c].dc_x;
+    return k;
+}
+
+// block-wide inclusive scan of affine maps (thread order), returns this thread's inclusive
+// prefix; *total gets the block aggregate.
+__device__ __forceinline__ Aff block_scan(Aff mine, Aff* total) {
+    __shared__ Aff warp_tot[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Aff inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Aff o;
+        o.a = __shfl_up_sync(0xffffffffu, inc.a, off);
+        o.b = __shfl_up_sync(0xffffffffu, inc.b, off);
+        if (lane >= off) inc = compose(o, inc);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    Aff pre{1.0, 0.0};
+    for (int w = 0; w < wid; ++w) pre = compose(pre, warp_tot[w]);
+    Aff all = pre;
+    for (int w = wid; w < kScanThreads / 32; ++w) all = compose(all, warp_tot[w]);
+    *total = all;
+    __syncthreads();
+    return compose(pre, inc);
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const TailParams p, int pass) {
+    const int c = blockIdx.y;
+    const TailChan ch = p.chan[c];
+    const ScanCtx k = make_ctx(p, c, pass, ch);
+    if (k.kind == SCAN_NONE) return;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPer;
+    Aff mine{1.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i)
+        if (base + i < p.n) mine = compose(mine, scan_elem(p, k, base + i));
+    Aff tot;
+    block_scan(mine, &tot);
+    if (threadIdx.x == 0) p.agg[(size_t)c * p.ntiles + blockIdx.x] = make_double2(tot.a, tot.b);
+}
+
+// one thread per channel: serial walk over the tile aggregates
+__global__ void k_scan_carry(const TailParams p, int pass) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.nchan) return;
+    const TailChan ch = p.chan[c];
+    const int kind = scan_kind(ch, pass);
+    if (kind == SCAN_NONE) return;
+    double v = 0.0;
+    if (!p.fresh) {
+        if (kind == SCAN_DEEMPH) v = p.state[c].deemph_z;
+        else if (kind == SCAN_DC) v = (double)p.state[c].dc_y;
+    }
+    if (kind == SCAN_AGC) v = 1.0;
+    double2* agg = p.agg + (size_t)c * p.ntiles;
+    for (int64_t t = 0; t < p.ntiles; ++t) {
+        const double2 ab = agg[t];
+        agg[t].x = v;                    // becomes the carry-in of tile t
+        v = fma(ab.x, v, ab.y);
+    }
+    if (kind == SCAN_DEEMPH) p.state[c].deemph_z = v;
+    else if (kind == SCAN_DC) p.state[c].dc_y = (float)v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TailParams p, int pass) {
+    const int c = blockIdx.y;
+    const TailChan ch = p.chan[c];
+    const ScanCtx k = make_ctx(p, c, pass, ch);
+    if (k.kind == SCAN_NONE) return;
+    const bool fin = scan_is_final(ch, pass, k.kind);
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPer;
+    Aff el[kScanPer];
+    Aff mine{1.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {
+        el[i] = Aff{1.0, 0.0};
+        if (base + i < p.n) el[i] = scan_elem(p, k, base + i);
+        mine = compose(mine, el[i]);
+    }
+    Aff tot;
+    const Aff inc = block_scan(mine, &tot);
+    // exclusive prefix of this thread = inclusive prefix of the previous thread
+    Aff exc;
+    exc.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+    exc.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    __shared__ Aff last_of_warp[kScanThreads / 32];
+    if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) exc = threadIdx.x == 0 ? Aff{1.0, 0.0} : last_of_warp[(threadIdx.x >> 5) - 1];
+    const double carry = p.agg[(size_t)c * p.ntiles + blockIdx.x].x;
+    double v = fma(exc.a, carry, exc.b);
+
+    float peak = 0.f;
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {
+        const int64_t r = base + i;
+        if (r >= p.n) break;
+        const double v_new = fma(el[i].a, v, el[i].b);
+        const float y = scan_emit(k, r, v, v_new);
+        v = v_new;
+        if (!fin) {
+            p.tmp[(size_t)c * p.work_stride + r] = y;
+            continue;
+        }
+        if (r < p.n_skip) continue;                               // warm-up rows are not emitted
+        const int64_t o = r - p.n_skip;
+        if (p.audio) p.audio[(size_t)c * p.out_stride + o] = y;
+        if (p.clipped) p.clipped[(size_t)c * p.out_stride + o] = fminf(fmaxf(y, -0.99f), 0.99f);   // processing.py:452
+        peak = fmaxf(peak, fabsf(y));
+        if (p.sumsq) {
+            int64_t w = ((p.mg0 + r) * (int64_t)p.decim - p.seg_origin) / p.seg_len - p.win0;
+            if (w < 0) w = 0;
+            if (w >= p.nwin) w = p.nwin - 1;
+            atomicAdd(p.sumsq + (size_t)c * p.nwin + w, (double)y * (double)y);
+        }
+    }
+    if (fin) {
+        // running pre-clip peak (processing.py:449-451); non-negative floats order like their bit patterns
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, off));
+        if ((threadIdx.x & 31) == 0 && peak > 0.f)
+            atomicMax(reinterpret_cast<unsigned int*>(&p.state[c].peak), __float_as_uint(peak));
+    }
+}
+
+// carried quantities that are plain copies of the last row
+__global__ void k_state_tail(const TailParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.nchan || p.n <= 0) return;
+    const int mode = p.chan[c].mode;
+    if (!p.skip_pre) {
+        const float2 last = p.bb[(size_t)c * p.bb_stride + p.n - 1];
+        p.state[c].prev_re = last.x;
+        p.state[c].prev_im = last.y;
+    }
+    if (mode == MODE_AM || mode == MODE_USB || mode == MODE_LSB || mode == MODE_RAW_DC)
+        p.state[c].dc_x = p.pre[(size_t)c * p.work_stride + p.n - 1];
+}
+
+int launch_tail(const TailParams& p, bool any_agc, cudaStream_t st, int64_t* launches) {
+    if (p.n <= 0) return IQ2A_OK;
+    const dim3 gpre((unsigned)((p.n + 255) / 256), p.nchan);
+    if (!p.skip_pre) k_pre<<<gpre, 256, 0, st>>>(p);
+    const dim3 gscan((unsigned)p.ntiles, p.nchan);
+    const int npass = any_agc ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        k_scan_reduce<<<gscan, kScanThreads, 0, st>>>(p, pass);
+        k_scan_carry<<<(p.nchan + 63) / 64, 64, 0, st>>>(p, pass);
+        k_scan_apply<<<gscan, kScanThreads, 0, st>>>(p, pass);
+    }
+    k_state_tail<<<(p.nchan + 63) / 64, 64, 0, st>>>(p);
+    if (launches) *launches += 2 + 3 * npass;
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
+int64_t tail_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
+
+}  // namespace iq2a

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs and against the golden vectors recorded from the reference.
+
+Tolerances (BASELINE.json north_star):
+  * sample counts per chunk, decimation phase, chunk boundaries: exact
+  * float audio: max abs error <= 1e-4 full scale
+  * complex64 channel samples: <= 1e-6 (float32 transform path vs the reference's complex128)
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import iq_oracle as orc
+from tests import _cases
+
+pytestmark = pytest.mark.gpu
+
+AUDIO_TOL = 1e-4
+BB_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from iq_to_audio_b200 import _lib
+    if _lib.device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device; the product path has no CPU fallback")
+    import iq_to_audio_b200.decoders as gd
+    import iq_to_audio_b200.processing as gp
+    from iq_to_audio_b200.bank import ChannelBank, Target
+    return dict(gp=gp, gd=gd, ChannelBank=ChannelBank, Target=Target, lib=_lib)
+
+
+@pytest.fixture(scope="module")
+def sv():
+    return _cases.load("stage_vectors")
+
+
+# ------------------------------------------------------------------------------- stage level
+def test_gtable_matches_host_plan(gpu):
+    from iq_to_audio_b200 import plan as P
+    taps = orc.channel_taps(2.5e6, 12_500.0, 26)
+    for m_fft in (512, 1024):
+        pl = P.build_plan(2.5e6, 26, [P.ChannelSpec(25e3, taps, 1), P.ChannelSpec(-300e3, taps, -1)], m_fft=m_fft)
+        with gpu["ChannelBank"](2.5e6, 26, [gpu["Target"](25e3, taps, 1), gpu["Target"](-300e3, taps, -1)],
+                                fft_size=m_fft) as b:
+            assert (b.fft_size, b.overlap_rows, b.rows_per_block) == (m_fft, pl.vd, pl.ld)
+            assert np.abs(b.g_table() - pl.g_table).max() <= 1e-11
+
+
+def test_mixer_matches_reference(gpu, sv):
+    z = sv["mix_in"]
+    osc = gpu["gp"].ComplexOscillator(123_456.7, 2.4e6)
+    a = osc.mix(z[:17_000], -1)
+    assert osc.phase == float(sv["mix_phase_a"])                 # phase carry: same float64 expression
+    b = osc.mix(z[17_000:], -1)
+    assert osc.phase == float(sv["mix_phase_b"])
+    # LO from CUDA's float64 sincos rounded to float32: <= 1 ulp of the LO from numpy's
+    assert np.abs(a - sv["mix_out_a"]).max() <= 3e-7 and np.abs(b - sv["mix_out_b"]).max() <= 3e-7
+    assert np.mean(a == sv["mix_out_a"]) > 0.95                  # and almost always identical bits
+
+
+def test_mixer_with_unpack_formats(gpu):
+    rng = np.random.default_rng(5)
+    for codec, raw in (("pcm_s16le", rng.integers(-32768, 32767, 2 * 4097, dtype=np.int16)),
+                       ("pcm_u8", rng.integers(0, 255, 2 * 4097, dtype=np.uint8)),
+                       ("pcm_f32le", rng.normal(size=2 * 4097).astype(np.float32))):
+        for order in orc.IQ_ORDERS:
+            x = orc.order_iq(orc.unpack_interleaved(raw, codec), order)
+            st = orc.NcoState(increment=-0.1234, phase=1.25)
+            want = orc.nco_mix(st, x, 1)
+            got = np.empty_like(x)
+            lib = gpu["lib"]
+            lib.check(lib.load().iq2a_unpack_mix(raw.ctypes.data, x.size, lib.CODEC_IDS[codec], lib.ORDER_IDS[order],
+                                                 1.25, -0.1234, got.ctypes.data, 0))
+            assert np.abs(got - want).max() <= 3e-7 * max(1.0, np.abs(want).max()), (codec, order)
+
+
+def test_fir_ragged_calls_match_reference(gpu, sv):
+    z = sv["mix_in"]
+    fir = gpu["gp"].OverlapSaveFIR(sv["fir_taps"], 4096)
+    out = np.concatenate([fir.process(z[:5_000]), fir.process(z[5_000:5_700]), fir.process(z[5_700:])])
+    assert out.size == z.size
+    assert np.abs(out - sv["fir_out"]).max() <= 1e-7
+    np.testing.assert_array_equal(fir.state, sv["fir_state"])
+
+
+def test_decimator_known_answers(gpu, sv):
+    Decimator = gpu["gp"].Decimator
+    d3 = Decimator(3)
+    got = np.concatenate([d3.process(np.arange(9, dtype=np.complex64)), d3.process(np.arange(9, 18, dtype=np.complex64))])
+    np.testing.assert_array_equal(got, np.arange(0, 18, 3, dtype=np.complex64))   # ref tests/test_processing.py:22-28
+    z = sv["mix_in"]
+    d7 = Decimator(7)
+    got = np.concatenate([d7.process(z[:10]), d7.process(z[10:11]), d7.process(z[11:400])])
+    np.testing.assert_array_equal(got, sv["dec7"])
+    assert d7.offset == int(sv["dec7_offset"])
+    assert Decimator(1).process(z[:5]) is not None and Decimator(1).process(z[:5]).size == 5
+
+
+def test_discriminator_deemphasis_dc_agc(gpu, sv):
+    gd = gpu["gd"]
+    from iq_to_audio_b200.decoders.base import run_scan
+    from iq_to_audio_b200.decoders.common import DCBlocker
+    from iq_to_audio_b200.decoders.nfm import DeemphasisFilter, QuadratureDemod
+    z = sv["mix_in"]
+    qd = QuadratureDemod()
+    a = np.concatenate([qd.process(z[:9_000]), qd.process(z[9_000:20_000])])
+    assert a.size == 20_000 and np.abs(a - sv["disc"]).max() <= 1e-6           # atan2f vs numpy arctan2: ulps
+    de = DeemphasisFilter(300.0, 96_153.846)
+    assert de.alpha == float(sv["deemph_alpha"])
+    y = np.concatenate([de.process(sv["disc"][:9_000]), de.process(sv["disc"][9_000:])])
+    assert np.abs(y - sv["deemph"]).max() <= 1e-7
+    assert abs(de.state - float(sv["deemph_state"])) <= 1e-12
+    dc = DCBlocker()
+    r = sv["dc_in"]
+    y = np.concatenate([dc.process(r[:2_500]), dc.process(r[2_500:])])
+    assert np.abs(y - sv["dc_out"]).max() <= 1e-6                               # float64 scan vs float32 loop
+    # AGC alone on the reference's own DC-blocked audio (identical input): float64 affine scan vs the
+    # reference's float32 sequential loop
+    fresh = gpu["lib"].ChannelState.fresh
+    g = np.concatenate([run_scan(2, 0.0, sv["dc_out"][:2_500], fresh()), run_scan(2, 0.0, sv["dc_out"][2_500:], fresh())])
+    ref = sv["agc_out"]
+    assert np.abs(g - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    assert np.abs(np.clip(g, -0.99, 0.99) - np.clip(ref, -0.99, 0.99)).max() <= AUDIO_TOL
+
+
+def test_decoder_plugins_match_oracle(gpu):
+    rng = np.random.default_rng(11)
+    n = 50_000
+    t = np.arange(n)
+    s = (0.3 * np.exp(1j * (0.02 * t + 2.0 * np.sin(0.004 * t))) * (1.0 + 0.5 * np.sin(0.01 * t))
+         + 0.01 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
+    for mode, agc in (("nfm", True), ("am", True), ("usb", False), ("lsb", False)):
+        dec = gpu["gd"].create_decoder(mode, deemph_us=300.0, agc_enabled=agc)
+        dec.setup(96_000.0)
+        st = orc.DemodState.create(mode, 96_000.0, deemph_us=300.0, agc_enabled=agc)
+        for lo, hi in ((0, 20_000), (20_000, 20_001), (20_001, n)):
+            got, stats = dec.process(s[lo:hi])
+            want, db = orc.demodulate(st, s[lo:hi])
+            assert got.size == want.size
+            assert np.abs(got - want).max() <= 2e-6, mode
+            assert abs(stats.rms_dbfs - db) <= 1e-3
+        assert dec.process(s[:0])[0].size == 0
+
+
+def test_choose_mix_sign_known_answers(gpu):
+    taps = orc.channel_taps(1e6, 12_500.0, 10)
+    nn = np.arange(0, int(1e6 * 0.1))
+    warm = np.exp(1j * 2.0 * np.pi * 12_500.0 * nn / 1e6).astype(np.complex64)
+    choose = gpu["gp"].choose_mix_sign
+    assert choose(warm, 1e6, 12_500.0, taps, 10) == 1            # ref tests/test_processing.py:31-40
+    assert choose(np.conj(warm), 1e6, 12_500.0, taps, 10) == -1
+    assert choose(warm[:0], 1e6, 12_500.0, taps, 10) == 1
+
+
+# ------------------------------------------------------------------------------- fused path
+def _targets(gpu, key, names):
+    m = _cases.manifest()[key]
+    fs = m["fs"]
+    d, _ = orc.plan_decimation(fs, 96_000.0)
+    gold = [_cases.load(n) for n in names]
+    tg = []
+    for t, g in zip(m["targets"], gold):
+        bw = t.get("bw", 12_500.0 if t["mode"] == "nfm" else 2_800.0)
+        tg.append(gpu["Target"](t["f_off"], orc.channel_taps(fs, bw, d), int(g["mix_sign"]), t["mode"], 300.0,
+                                t.get("agc", True)))
+    return m, fs, d, tg, gold
+
+
+def _stream(gpu, key, names, fft_size=0, limit=None):
+    m, fs, d, tg, gold = _targets(gpu, key, names)
+    raw = _cases.raw_input(key).view(np.uint8)
+    fb = orc.FRAME_BYTES[m["codec"]]
+    chunk = m["chunk"]
+    nfr = raw.size // fb if limit is None else min(raw.size // fb, limit)
+    out = dict(audio=[], clipped=[], bb=[], counts=[], rms=[])
+    with gpu["ChannelBank"](fs, d, tg, codec=m["codec"], iq_order=m["iq_order"], ref_chunk=chunk,
+                            fft_size=fft_size) as bank:
+        for s in range(0, nfr, chunk):
+            r = bank.process_chunk(raw[s * fb:min(s + chunk, nfr) * fb], want_baseband=True)
+            out["audio"].append(r.audio.copy()); out["clipped"].append(r.clipped.copy())
+            out["bb"].append(r.baseband.copy()); out["counts"].append(r.count); out["rms"].append(r.rms_dbfs.copy())
+        peaks = bank.peaks
+        consumed = bank.get_state()[1]
+    assert consumed == nfr
+    cat = {k: np.concatenate(out[k], axis=1) for k in ("audio", "clipped", "bb")}
+    return cat, out["counts"], np.asarray(out["rms"]), peaks, gold
+
+
+def _check(cat, counts, rms, peaks, gold, audio_tol=AUDIO_TOL):
+    for i, g in enumerate(gold):
+        assert counts == list(g["counts"])                                    # exact chunk boundaries
+        assert np.abs(cat["bb"][i] - g["baseband"]).max() <= BB_TOL
+        assert np.abs(cat["audio"][i] - g["audio"]).max() <= audio_tol
+        assert np.abs(cat["clipped"][i] - g["clipped"]).max() <= audio_tol
+        assert np.abs(rms[:, i] - g["rms_dbfs"]).max() <= 1e-3
+        assert abs(peaks[i] - float(g["peak"])) <= audio_tol * max(1.0, float(g["peak"]))
+
+
+@pytest.mark.parametrize("fft_size", [512, 1024])
+def test_stream_case_a_benchmark_shape(gpu, fft_size):
+    _check(*_stream(gpu, "case_a_nfm_2p5M", ["case_a_nfm_2p5M"], fft_size))
+
+
+@pytest.mark.parametrize("fft_size", [512, 1024])
+def test_stream_case_b_five_nfm_targets(gpu, fft_size):
+    _check(*_stream(gpu, "case_b_nfm_10M", [f"case_b_nfm_10M_t{i}" for i in range(5)], fft_size))
+
+
+def test_stream_case_c_am_target(gpu):
+    m, fs, d, tg, gold = _targets(gpu, "case_c_20M_am_ssb", ["case_c_20M_am", "case_c_20M_usb", "case_c_20M_lsb"])
+    cat, counts, rms, peaks, gold = _stream(gpu, "case_c_20M_am_ssb", ["case_c_20M_am", "case_c_20M_usb", "case_c_20M_lsb"])
+    _check({k: v[:1] for k, v in cat.items()}, counts, rms[:, :1], peaks[:1], gold[:1])
+    # SSB channels: channel samples are within tolerance for every target
+    for i in (1, 2):
+        assert np.abs(cat["bb"][i] - gold[i]["baseband"]).max() <= BB_TOL
+
+
+@pytest.mark.parametrize("name", ["case_d_pcm_u8_qi_nfm", "case_d_pcm_f32le_iq_inv_nfm", "case_d_pcm_s16le_qi_inv_usb"])
+def test_stream_case_d_formats_and_iq_order(gpu, name):
+    _check(*_stream(gpu, name, [name]))
+
+
+def test_stream_case_e_preview_truncation(gpu):
+    m = _cases.manifest()["case_e_truncated"]
+    _cases.manifest()["case_e_truncated"].setdefault("fs", 2.5e6)
+    m.setdefault("codec", "pcm_s16le"); m.setdefault("iq_order", "iq")
+    m.setdefault("targets", [dict(f_off=25e3, bw=12_500.0, mode="nfm")])
+    _check(*_stream(gpu, "case_e_truncated", ["case_e_truncated"], limit=m["max_input_samples"]))
+
+
+def test_chunk_split_invariance_and_state_roundtrip(gpu):
+    """Feeding the same capture in different call sizes gives the same audio (NFM has no per-chunk
+    semantics); get_state/set_state moves the carried decoder state between banks."""
+    m, fs, d, tg, gold = _targets(gpu, "case_a_nfm_2p5M", ["case_a_nfm_2p5M"])
+    raw = _cases.raw_input("case_a_nfm_2p5M")
+    n = raw.size // 2
+    outs = []
+    for sizes in ([n], [1, 25, 26, 27, 100_003, n]):
+        with gpu["ChannelBank"](fs, d, tg, ref_chunk=65_536) as bank:
+            pos, parts = 0, []
+            for sz in sizes:
+                e = min(n, pos + sz)
+                if e > pos:
+                    parts.append(bank.process_chunk(raw[2 * pos:2 * e]).audio[0].copy())
+                pos = e
+            if pos < n:
+                parts.append(bank.process_chunk(raw[2 * pos:]).audio[0].copy())
+            outs.append(np.concatenate(parts))
+    assert outs[0].size == outs[1].size == gold[0]["audio"].size
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-6
+    assert np.abs(outs[0] - gold[0]["audio"]).max() <= AUDIO_TOL
+
+
+def test_resident_whole_capture_and_time_shards(gpu):
+    """The resident API on the whole capture, then as two time shards (halo + 600-row warm-up):
+    both reproduce the reference's single-stream audio."""
+    import torch
+    key = "case_b_nfm_10M"
+    names = [f"case_b_nfm_10M_t{i}" for i in range(5)]
+    m, fs, d, tg, gold = _targets(gpu, key, names)
+    raw = _cases.raw_input(key)
+    n = raw.size // 2
+    d_raw = torch.from_numpy(raw.copy()).cuda()
+    chunk = m["chunk"]
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=chunk) as bank:
+        rows = bank.rows_in(0, n)
+        d_audio = torch.zeros((5, rows), dtype=torch.float32, device="cuda")
+        d_clip = torch.zeros((5, rows), dtype=torch.float32, device="cuda")
+        d_bb = torch.zeros((5, rows), dtype=torch.complex64, device="cuda")
+        k, rms = bank.process_resident(d_raw.data_ptr(), 0, n, 0, n, dev_audio=d_audio.data_ptr(),
+                                       dev_clipped=d_clip.data_ptr(), dev_baseband=d_bb.data_ptr(),
+                                       out_stride=rows, want_rms=True)
+        assert k == rows == gold[0]["audio"].size
+        a, c, b = d_audio.cpu().numpy(), d_clip.cpu().numpy(), d_bb.cpu().numpy()
+        for i, g in enumerate(gold):
+            assert np.abs(a[i] - g["audio"]).max() <= AUDIO_TOL
+            assert np.abs(c[i] - g["clipped"]).max() <= AUDIO_TOL
+            assert np.abs(b[i] - g["baseband"]).max() <= BB_TOL
+            assert np.abs(rms[i] - g["rms_dbfs"]).max() <= 1e-3
+        peaks = bank.peaks
+        for i, g in enumerate(gold):
+            assert abs(peaks[i] - float(g["peak"])) <= 1e-6
+        # two shards, the second starts at a reference-chunk boundary with its own halo
+        half = 2 * chunk
+        r0 = bank.rows_in(0, half)
+        bank.process_resident(d_raw.data_ptr(), 0, n, 0, half, dev_audio=d_audio.data_ptr(), out_stride=rows)
+        a0 = d_audio.cpu().numpy()[:, :r0].copy()
+        first = half - bank.halo - 601 * d
+        view = d_raw[2 * first:]
+        bank.process_resident(view.data_ptr(), first, n - first, half, n, warmup_rows=600,
+                              dev_audio=d_audio.data_ptr(), out_stride=rows)
+        a1 = d_audio.cpu().numpy()[:, :rows - r0]
+        both = np.concatenate([a0, a1], axis=1)
+        for i, g in enumerate(gold):
+            assert np.abs(both[i] - g["audio"]).max() <= AUDIO_TOL
+        # missing halo is an error, not a silent zero-fill
+        with pytest.raises(ValueError, match="history"):
+            bank.process_resident(d_raw[2 * half:].data_ptr(), half, n - half, half, n, warmup_rows=600,
+                                  dev_audio=d_audio.data_ptr(), out_stride=rows)
+
+
+def test_linearity_and_channel_independence_at_scale(gpu):
+    """Size-independent properties on a larger capture (32 Mi samples, device-generated):
+    (1) a channel's output does not depend on which other channels share the bank;
+    (2) channel samples are linear in the input: bank(a) + bank(b) == bank(a+b) for complex64 input."""
+    import torch
+    fs, d = 10e6, 104
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    n = 1 << 22
+    rng = np.random.default_rng(3)
+    t = np.arange(n) / fs
+    a = (0.2 * np.exp(2j * np.pi * 400e3 * t) + 0.02 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
+    b = (0.1 * np.exp(2j * np.pi * (400e3 + 700.0) * t)).astype(np.complex64)
+    T = gpu["Target"]
+
+    def run(x, targets):
+        with gpu["ChannelBank"](fs, d, targets, codec="complex64", ref_chunk=1 << 20) as bank:
+            return bank.process_chunk(x, want_baseband=True).baseband
+    both = run(a, [T(400e3, taps, 1, "iq"), T(-2.5e6, taps, 1, "iq"), T(3.3e6, taps, -1, "iq")])
+    alone = run(a, [T(400e3, taps, 1, "iq")])
+    assert np.abs(both[0] - alone[0]).max() <= 1e-6
+    sa, sb, sab = alone[0], run(b, [T(400e3, taps, 1, "iq")])[0], run((a + b).astype(np.complex64), [T(400e3, taps, 1, "iq")])[0]
+    assert np.abs(sa + sb - sab).max() <= 2e-6
