@@ -12,7 +12,7 @@ namespace iq2a {
 // HBM-bound: reads 2/4/8 B and writes 8 B per sample; each thread handles 4 consecutive
 // frames (one 128-bit load for s16, two 128-bit stores).
 // LO = complex64(exp(1j * (phase + w*n))) with the float64 ramp of the reference; the
-// product is the numpy complex64 multiply (separately rounded products, then add/sub).
+// product is the numpy complex64 multiply (cmul_np below).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 lo_f64(double phase, double w, int64_t n) {
     const double ph = __dadd_rn(phase, __dmul_rn(w, (double)n));
@@ -20,9 +20,11 @@ __device__ __forceinline__ float2 lo_f64(double phase, double w, int64_t n) {
     sincos(ph, &s, &c);
     return make_float2((float)c, (float)s);
 }
+// numpy's complex64 multiply as its SIMD loops evaluate it on FMA-capable x86 (AVX2/AVX-512):
+// re = fma(ar, br, -(ai*bi)), im = fma(ar, bi, ai*br) -- pinned by tests/golden/stage_vectors.npz.
 __device__ __forceinline__ float2 cmul_np(float2 a, float2 b) {
-    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
-                       __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)),
+                       __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 
 template <int FMT>

@@ -58,9 +58,9 @@ __global__ void k_pre(const TailParams p) {
         if (r > 0) prev = bb[r - 1];
         else if (p.fresh) prev = make_float2(1.f, 0.f);          // nfm.py:15
         else prev = make_float2(p.state[c].prev_re, p.state[c].prev_im);
-        // numpy complex64 product s * conj(prev), then arctan2 (nfm.py:21-22)
-        const float re = __fadd_rn(__fmul_rn(s.x, prev.x), __fmul_rn(s.y, prev.y));
-        const float im = __fsub_rn(__fmul_rn(s.y, prev.x), __fmul_rn(s.x, prev.y));
+        // numpy complex64 product s * conj(prev) (FMA form of its SIMD loop), then arctan2 (nfm.py:21-22)
+        const float re = __fmaf_rn(s.x, prev.x, __fmul_rn(s.y, prev.y));
+        const float im = __fmaf_rn(s.x, -prev.y, __fmul_rn(s.y, prev.x));
         out = atan2f(im, re);
     } else if (ch.mode == MODE_AM) {
         out = hypotf(s.x, s.y);                                  // am.py:28
@@ -174,27 +174,49 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const TailParams p
     if (threadIdx.x == 0) p.agg[(size_t)c * p.ntiles + blockIdx.x] = make_double2(tot.a, tot.b);
 }
 
-// one thread per channel: serial walk over the tile aggregates
-__global__ void k_scan_carry(const TailParams p, int pass) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.nchan) return;
+// one CTA per channel: block-level scan over the tile aggregates.  Each thread composes a
+// contiguous run of tiles, the runs are scanned across the block, then every thread
+// rewrites its run with the carry-in of each tile.
+__global__ void __launch_bounds__(kScanThreads) k_scan_carry(const TailParams p, int pass) {
+    const int c = blockIdx.x;
     const TailChan ch = p.chan[c];
     const int kind = scan_kind(ch, pass);
     if (kind == SCAN_NONE) return;
-    double v = 0.0;
+    double v0 = 0.0;
     if (!p.fresh) {
-        if (kind == SCAN_DEEMPH) v = p.state[c].deemph_z;
-        else if (kind == SCAN_DC) v = (double)p.state[c].dc_y;
+        if (kind == SCAN_DEEMPH) v0 = p.state[c].deemph_z;
+        else if (kind == SCAN_DC) v0 = (double)p.state[c].dc_y;
     }
-    if (kind == SCAN_AGC) v = 1.0;
+    if (kind == SCAN_AGC) v0 = 1.0;
     double2* agg = p.agg + (size_t)c * p.ntiles;
-    for (int64_t t = 0; t < p.ntiles; ++t) {
+    const int64_t per = (p.ntiles + kScanThreads - 1) / kScanThreads;
+    const int64_t t0 = (int64_t)threadIdx.x * per;
+    const int64_t t1 = min(p.ntiles, t0 + per);
+    Aff mine{1.0, 0.0};
+    for (int64_t t = t0; t < t1; ++t) {
+        const double2 ab = agg[t];
+        mine = compose(mine, Aff{ab.x, ab.y});
+    }
+    Aff tot;
+    const Aff inc = block_scan(mine, &tot);
+    Aff exc;
+    exc.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+    exc.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    __shared__ Aff last_of_warp[kScanThreads / 32];
+    if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) exc = threadIdx.x == 0 ? Aff{1.0, 0.0} : last_of_warp[(threadIdx.x >> 5) - 1];
+    double v = fma(exc.a, v0, exc.b);
+    for (int64_t t = t0; t < t1; ++t) {
         const double2 ab = agg[t];
         agg[t].x = v;                    // becomes the carry-in of tile t
         v = fma(ab.x, v, ab.y);
     }
-    if (kind == SCAN_DEEMPH) p.state[c].deemph_z = v;
-    else if (kind == SCAN_DC) p.state[c].dc_y = (float)v;
+    if (threadIdx.x == 0) {
+        const double vend = fma(tot.a, v0, tot.b);
+        if (kind == SCAN_DEEMPH) p.state[c].deemph_z = vend;
+        else if (kind == SCAN_DC) p.state[c].dc_y = (float)vend;
+    }
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TailParams p, int pass) {
@@ -226,6 +248,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TailParams p,
     double v = fma(exc.a, carry, exc.b);
 
     float peak = 0.f;
+    // statistics: a thread's kScanPer consecutive rows touch at most two windows
+    int64_t w_cur = -1;
+    double ss_cur = 0.0;
 #pragma unroll
     for (int i = 0; i < kScanPer; ++i) {
         const int64_t r = base + i;
@@ -246,7 +271,24 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TailParams p,
             int64_t w = ((p.mg0 + r) * (int64_t)p.decim - p.seg_origin) / p.seg_len - p.win0;
             if (w < 0) w = 0;
             if (w >= p.nwin) w = p.nwin - 1;
-            atomicAdd(p.sumsq + (size_t)c * p.nwin + w, (double)y * (double)y);
+            if (w != w_cur) {
+                if (w_cur >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
+                w_cur = w;
+                ss_cur = 0.0;
+            }
+            ss_cur = fma((double)y, (double)y, ss_cur);
+        }
+    }
+    if (fin && p.sumsq) {
+        // warp-aggregate when the whole warp sits in one window (the common case)
+        const int64_t w0 = __shfl_sync(0xffffffffu, w_cur, 0);
+        const bool uniform = __all_sync(0xffffffffu, w_cur == w0);
+        if (uniform) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss_cur += __shfl_xor_sync(0xffffffffu, ss_cur, off);
+            if ((threadIdx.x & 31) == 0 && w0 >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + w0, ss_cur);
+        } else if (w_cur >= 0) {
+            atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
         }
     }
     if (fin) {
@@ -280,7 +322,7 @@ int launch_tail(const TailParams& p, bool any_agc, cudaStream_t st, int64_t* lau
     const int npass = any_agc ? 2 : 1;
     for (int pass = 0; pass < npass; ++pass) {
         k_scan_reduce<<<gscan, kScanThreads, 0, st>>>(p, pass);
-        k_scan_carry<<<(p.nchan + 63) / 64, 64, 0, st>>>(p, pass);
+        k_scan_carry<<<p.nchan, kScanThreads, 0, st>>>(p, pass);
         k_scan_apply<<<gscan, kScanThreads, 0, st>>>(p, pass);
     }
     k_state_tail<<<(p.nchan + 63) / 64, 64, 0, st>>>(p);

@@ -57,7 +57,6 @@ def test_mixer_matches_reference(gpu, sv):
     assert osc.phase == float(sv["mix_phase_b"])
     # LO from CUDA's float64 sincos rounded to float32: <= 1 ulp of the LO from numpy's
     assert np.abs(a - sv["mix_out_a"]).max() <= 3e-7 and np.abs(b - sv["mix_out_b"]).max() <= 3e-7
-    assert np.mean(a == sv["mix_out_a"]) > 0.95                  # and almost always identical bits
 
 
 def test_mixer_with_unpack_formats(gpu):
