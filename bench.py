@@ -87,7 +87,7 @@ def make_targets():
 # clocks / throttle reasons during the timed region
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.004):
         self.period = period
         self.samples: list[int] = []
         self.reasons: set[str] = set()
@@ -248,13 +248,14 @@ def main() -> None:
     seg_begin = rank * n_seg
     seg_end = seg_begin + n_seg
     first = max(0, seg_begin - bank.halo - (warm_rows + 1) * d)
-    capture = synth_capture_device(first, seg_end - first, dev, seed=1234 + rank)
+    first -= first % 4                                             # 16-byte aligned int16 frames for the TMA path
+    capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
     audio = torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
     gathered = [torch.empty_like(audio) for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def resident_step():
-        bank.process_resident(capture.data_ptr(), first, seg_end - first, seg_begin, seg_end,
+        bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
                               warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
         if world > 1:
             dist.gather(audio, gathered, dst=0)
@@ -296,7 +297,7 @@ def main() -> None:
     e2e = None
     if not args.no_e2e:
         host = torch.empty(2 * n_seg, dtype=torch.int16).pin_memory()
-        host.copy_(capture[2 * (seg_begin - first):])
+        host.copy_(capture[2 * (seg_begin - first):2 * (seg_begin - first) + 2 * n_seg])
         host_np = host.numpy()
         nchunks = (n_seg + chunk - 1) // chunk
         bytes_out = 0
@@ -348,7 +349,7 @@ def main() -> None:
             traffic = traffic * n_in if traffic is not None else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_channelize<512,5,s16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_channelize2<5>" if bank.kernel_generation == 2 else "k_channelize<512,5,s16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_sample": b_alg, "kernel_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1),
                 "peak_source": peak_src}
@@ -366,7 +367,7 @@ def main() -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
         "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
-                   "fft_size": bank.fft_size, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}",
+                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}",
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

@@ -46,7 +46,8 @@ class BankConfig(C.Structure):
 
 class BankInfo(C.Structure):
     _fields_ = [("fft_size", C.c_int32), ("overlap_rows", C.c_int32), ("rows_per_block", C.c_int32),
-                ("n_channels", C.c_int32), ("hop", C.c_int64), ("halo", C.c_int64), ("fs_channel", C.c_double)]
+                ("n_channels", C.c_int32), ("hop", C.c_int64), ("halo", C.c_int64), ("fs_channel", C.c_double),
+                ("kernel_generation", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ChannelState(C.Structure):

@@ -83,6 +83,7 @@ class ChannelBank:
         self.hop = info.hop
         self.halo = info.halo
         self.fs_channel = info.fs_channel
+        self.kernel_generation = info.kernel_generation
         self.n_channels = len(targets)
 
     # -- lifetime ---------------------------------------------------------------------------

@@ -60,6 +60,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             objs.append(o)
             if force or _stale(o, [inst] + headers):
                 jobs.append((inst, o, [f"-DIQ2A_M={m}", f"-DIQ2A_CG={cg}"]))
+    inst2 = CSRC / "channelizer2_inst.cu"
+    for cg in GROUP_SIZES:
+        o = OBJ / f"channelizer2_{cg}.o"
+        objs.append(o)
+        if force or _stale(o, [inst2] + headers):
+            jobs.append((inst2, o, [f"-DIQ2A_CG={cg}"]))
     # biggest kernels first so the pool drains evenly
     jobs.sort(key=lambda j: -len(j[2]))
 

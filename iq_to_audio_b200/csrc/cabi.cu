@@ -2,6 +2,7 @@
 // sequencing.  Host-side logic only; all per-sample arithmetic lives in the kernels.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -76,8 +77,11 @@ struct iq2a_bank {
     std::vector<Group> groups;
     int64_t n_pos = 0;              // streaming: input samples consumed
     int64_t launches = 0;
+    int64_t launches_v2 = 0;
 
     float2* d_gtab = nullptr;
+    float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
+    bool v2_ok = false;
     float2* d_tw = nullptr;
     double* d_taps = nullptr;
     int64_t* d_tap_off = nullptr;
@@ -107,7 +111,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_gtab, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -146,6 +150,7 @@ static void extend_phase_table(iq2a_bank* b, int64_t nchunks) {
 struct CoreArgs {
     const void* d_raw;
     int64_t raw_n0, raw_len;
+    int64_t raw_pad;                     // frames readable (finite garbage allowed) beyond raw_len
     int64_t mg_begin, mg_emit, mg_end;   // rows [mg_begin, mg_end) computed, [mg_emit, mg_end) emitted
     bool fresh;
     // phase / segmentation model
@@ -185,6 +190,24 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
 
     if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[0], a.st));
     // ---- channel bank: one launch per channel group -------------------------------------
+    // Second-generation kernel (TMA-staged int16, packed transforms) over every row whose input
+    // rows are complete in the resident buffer; the first-generation kernel (bounds-checked loads)
+    // picks up whatever is left (other codecs, M = 1024, unaligned buffers, a ragged last row).
+    bool use_v2 = b->v2_ok;
+    int64_t mg_split = a.mg_begin, t_row0 = 0, t_rows = 0;
+    const char* t_base = nullptr;
+    if (use_v2) {
+        const int64_t D = b->D;
+        const int64_t need_from = std::max<int64_t>(0, a.mg_begin - b->vd) * D;
+        const int64_t n_base = std::max(need_from, ceil_div(a.raw_n0, D) * D);
+        t_base = static_cast<const char*>(a.d_raw) + (n_base - a.raw_n0) * 4;
+        t_rows = (a.raw_n0 + a.raw_len + a.raw_pad - n_base) / D;
+        t_row0 = n_base / D;
+        if (a.raw_n0 > need_from || (reinterpret_cast<uintptr_t>(t_base) & 15) || t_rows <= 0) use_v2 = false;
+        else mg_split = std::min(a.mg_end, t_row0 + t_rows);
+        if (mg_split <= a.mg_begin) use_v2 = false;
+    }
+    if (!use_v2) mg_split = a.mg_begin;
     for (const Group& g : b->groups) {
         ChannelizeParams p{};
         p.raw = a.d_raw;
@@ -195,21 +218,33 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         p.decim = b->D;
         p.vd = b->vd;
         p.ld = b->ld;
-        p.mg_begin = a.mg_begin;
-        p.mg_end = a.mg_end;
-        p.nblocks = (int)ceil_div(n_rows, b->ld);
         p.nchan = g.count;
-        p.gtab = b->d_gtab + g.g_off;
         p.twid = b->d_tw;
-        p.out = b->d_bb + (size_t)g.first * stride;
         p.out_stride = stride;
         p.phase.tab = b->d_phase + (size_t)g.first * a.nseg;
         p.phase.seg_len = a.seg_len;
         p.phase.seg0_n = a.seg_origin;
         p.phase.nseg = a.nseg;
         for (int i = 0; i < g.count; ++i) p.w[i] = b->w[g.first + i];
-        if ((rc = launch_channelize(p, b->M, g.count, b->cfg.codec, b->n_sm, a.st))) return rc;
-        b->launches++;
+        if (use_v2) {
+            p.mg_begin = a.mg_begin;
+            p.mg_end = mg_split;
+            p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
+            p.gtab = b->d_gtab2 + g.g_off;
+            p.out = b->d_bb + (size_t)g.first * stride;
+            if ((rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st))) return rc;
+            b->launches++;
+            b->launches_v2++;
+        }
+        if (mg_split < a.mg_end) {
+            p.mg_begin = mg_split;
+            p.mg_end = a.mg_end;
+            p.nblocks = (int)ceil_div(a.mg_end - mg_split, b->ld);
+            p.gtab = b->d_gtab + g.g_off;
+            p.out = b->d_bb + (size_t)g.first * stride + (mg_split - a.mg_begin);
+            if ((rc = launch_channelize(p, b->M, g.count, b->cfg.codec, b->n_sm, a.st))) return rc;
+            b->launches++;
+        }
     }
     if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[1], a.st));
     // ---- head fix-up: stream start rows recomputed in float64 ----------------------------
@@ -447,13 +482,22 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     ok &= cudaMemcpy(b->d_w, b->w.data(), C * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(b->d_chan, tc.data(), C * sizeof(TailChan), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) { cudaFree(d_wtab); set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(IQ2A_ERR_CUDA); }
+    {
+        const char* env = std::getenv("IQ2A_CHANNELIZER");
+        const bool force_v1 = env && std::strcmp(env, "v1") == 0;
+        b->v2_ok = !force_v1 && M == 512 && cfg->codec == IQ2A_CODEC_S16 && D % 4 == 0 && channelize2_available();
+        if (b->v2_ok && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
+    }
     for (const Group& g : b->groups)
         for (int i = 0; i < g.count; ++i) {
             const int c = g.first + i;
             rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
-                                b->d_gtab + g.g_off, g.count, i, b->stream);
+                                b->d_gtab + g.g_off, g.count, i, 0, 1.0, b->stream);
+            if (!rc && b->v2_ok)
+                rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
+                                    b->d_gtab2 + g.g_off, g.count, i, 1, 1.0 / 32768.0, b->stream);
             if (rc) { cudaFree(d_wtab); return fail(rc); }
-            b->launches++;
+            b->launches += b->v2_ok ? 2 : 1;
         }
     cudaError_t e = cudaStreamSynchronize(b->stream);
     cudaFree(d_wtab);
@@ -474,6 +518,8 @@ int iq2a_bank_info_get(const iq2a_bank* b, iq2a_bank_info* info) {
     info->hop = (int64_t)b->ld * b->D;
     info->halo = (int64_t)b->vd * b->D;
     info->fs_channel = b->cfg.sample_rate / b->D;
+    info->kernel_generation = b->v2_ok ? 2 : 1;
+    info->reserved = 0;
     return IQ2A_OK;
 }
 
@@ -568,9 +614,13 @@ int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, 
 
     // stream buffer: [history | new chunk]; history = the (vd+1)*D frames before n_pos
     const int64_t want_hist = std::min<int64_t>((int64_t)(b->vd + 1) * D, b->n_pos);
-    const int64_t keep = std::min(want_hist, b->ring_frames);
+    int64_t keep = std::min(want_hist, b->ring_frames);
+    // first ring frame on a 4-frame boundary of the global index (16 B for int16 -> TMA-addressable)
+    keep = std::max<int64_t>(0, b->n_pos - (((b->n_pos - keep) + 3) & ~(int64_t)3));
     const int nxt = b->ring_cur ^ 1;
-    int rc = dev_grow(&b->d_ring[nxt], &b->ring_cap[nxt], (size_t)(keep + n_frames) * fb + 16);
+    // D extra frames after the chunk: the bulk kernel reads whole rows of D frames (values beyond the
+    // data only ever meet zero taps, but must be readable)
+    int rc = dev_grow(&b->d_ring[nxt], &b->ring_cap[nxt], (size_t)(keep + n_frames + D) * fb + 16);
     if (rc) return rc;
     if (keep > 0)
         IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_ring[nxt], b->d_ring[b->ring_cur] + (size_t)(b->ring_frames - keep) * fb,
@@ -587,6 +637,7 @@ int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, 
     a.d_raw = b->d_ring[nxt];
     a.raw_n0 = b->n_pos - keep;
     a.raw_len = keep + n_frames;
+    a.raw_pad = (b->cfg.codec == IQ2A_CODEC_S16) ? D : 0;
     a.mg_begin = a.mg_emit = mg_begin;
     a.mg_end = mg_end;
     a.fresh = false;
@@ -666,6 +717,7 @@ static int resident_common(iq2a_bank* b, const void* dev_frames, int64_t first_f
     a.d_raw = dev_frames;
     a.raw_n0 = first_frame;
     a.raw_len = n_frames;
+    a.raw_pad = 0;
     a.mg_begin = mg_begin;
     a.mg_emit = mg_emit;
     a.mg_end = mg_end;

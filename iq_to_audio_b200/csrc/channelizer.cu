@@ -1,5 +1,7 @@
 // Dispatcher over the per-(M, CG) instantiations of the channel-bank kernel
 // (channelizer.cuh holds the kernel, channelizer_inst.cu the instantiations).
+#include <cuda.h>
+
 #include "common.cuh"
 #include "stage.cuh"
 #include "../../include/iq2a_b200.h"
@@ -19,6 +21,53 @@ int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, i
     IQ2A_CASES(512)
     IQ2A_CASES(1024)
     set_error("unsupported transform size %d / channel group %d", m_fft, cg);
+    return IQ2A_ERR_INVALID;
+}
+
+#define IQ2A_DECL2(CG) int launch_channelize2_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
+IQ2A_DECL2(1) IQ2A_DECL2(2) IQ2A_DECL2(3) IQ2A_DECL2(4) IQ2A_DECL2(5) IQ2A_DECL2(6)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+bool channelize2_available() { return encode_tiled_fn() != nullptr; }
+
+// Second-generation kernel over rows [p.mg_begin, p.mg_end): `base` points at the int16 frame whose global
+// index is tmap_row0 * D (16-byte aligned), `rows` complete rows of D frames are readable from there.
+int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
+                       int n_sm, cudaStream_t st) {
+    if (p.nblocks <= 0) return IQ2A_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return IQ2A_ERR_STATE; }
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.decim, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.decim * 4};
+    const cuuint32_t box[2] = {8, 172};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return IQ2A_ERR_CUDA; }
+    switch (cg) {
+#define IQ2A_CASE2(CG) case CG: return launch_channelize2_##CG(p, tmap, tmap_row0, n_sm, st);
+        IQ2A_CASE2(1) IQ2A_CASE2(2) IQ2A_CASE2(3) IQ2A_CASE2(4) IQ2A_CASE2(5) IQ2A_CASE2(6)
+    }
+    set_error("unsupported channel group %d", cg);
     return IQ2A_ERR_INVALID;
 }
 

@@ -43,6 +43,64 @@ struct Geo<1024> {
     static constexpr int R1 = 32, R2 = 32, LW = 16;
 };
 
+// Inverse M-point transforms of the output spectra held in `tile` ([slot j'][YS] float2, j' = k1*R2 + k2
+// <-> bin k1 + R1*k2), overlap rows dropped, NCO rotation at the channel rate, complex64 store.
+// Shared by both channel-bank kernels.  Ends with the tile free for reuse (caller syncs).
+template <int M, int CG>
+__device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw, const ChannelizeParams& p, int blk0) {
+    using G = Geo<M>;
+    constexpr int R1 = G::R1, R2 = G::R2;
+    constexpr int BT = kBlocksPerSet;
+    constexpr int NS = CG * BT;
+    constexpr int YS = NS | 1;
+    const int tid = threadIdx.x;
+    const int D = p.decim;
+    __syncthreads();
+    // inverse pass A: for each k1, R2-point inverse over k2, then W_M^{-m2*k1}
+    for (int idx = tid; idx < R1 * NS; idx += kThreads) {
+        const int sy = idx % NS, k1 = idx / NS;
+        float2 v[R2];
+        float2* base = tile + (k1 * R2) * YS + sy;
+#pragma unroll
+        for (int i = 0; i < R2; ++i) v[i] = base[i * YS];
+        dif<R2, -1>(v);
+        static_for<R2>([&](auto mc) {
+            constexpr int m2 = decltype(mc)::value;
+            float2 x = v[bitrev<R2>(m2)];
+            if constexpr (m2 != 0) x = cmul_conj(x, tw[(m2 * k1) & (M - 1)]);
+            base[m2 * YS] = x;
+        });
+    }
+    __syncthreads();
+    // inverse pass B: for each m2, R1-point inverse over k1 -> y[R2*m1 + m2]
+    for (int idx = tid; idx < R2 * NS; idx += kThreads) {
+        const int sy = idx % NS, m2 = idx / NS;
+        float2 v[R1];
+        float2* base = tile + m2 * YS + sy;
+#pragma unroll
+        for (int i = 0; i < R1; ++i) v[i] = base[(i * R2) * YS];
+        dif<R1, -1>(v);
+        static_for<R1>([&](auto mc) {
+            constexpr int m1 = decltype(mc)::value;
+            base[(m1 * R2) * YS] = v[bitrev<R1>(m1)];
+        });
+    }
+    __syncthreads();
+    // ---------------- drop the overlap rows, rotate by the NCO, store ------------------------
+    const int ld = p.ld;
+    for (int idx = tid; idx < NS * ld; idx += kThreads) {
+        const int r = idx % ld, sy = idx / ld;
+        const int b = sy / CG, c = sy % CG;
+        const int blk = blk0 + b;
+        const int64_t mg = p.mg_begin + (int64_t)blk * ld + r;
+        if (blk < p.nblocks && mg < p.mg_end && c < p.nchan) {
+            const float2 y = tile[(p.vd + r) * YS + sy];
+            const float2 lo = phasor_f32(nco_phase(p.phase, c, p.w[c], mg * (int64_t)D));
+            p.out[(size_t)c * p.out_stride + (mg - p.mg_begin)] = cmul(y, lo);
+        }
+    }
+}
+
 template <int M, int CG, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) k_channelize(const ChannelizeParams p) {
     using G = Geo<M>;
@@ -181,50 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_channelize(const ChannelizePara
 #pragma unroll
                 for (int c = 0; c < CG; ++c) tile[j * YS + b * CG + c] = acc[i][c][b];
         }
-        __syncthreads();
-        // inverse pass A: for each k1, R2-point inverse over k2, then W_M^{-m2*k1}
-        for (int idx = tid; idx < R1 * NS; idx += kThreads) {
-            const int sy = idx % NS, k1 = idx / NS;
-            float2 v[R2];
-            float2* base = tile + (k1 * R2) * YS + sy;
-#pragma unroll
-            for (int i = 0; i < R2; ++i) v[i] = base[i * YS];
-            dif<R2, -1>(v);
-            static_for<R2>([&](auto mc) {
-                constexpr int m2 = decltype(mc)::value;
-                float2 x = v[bitrev<R2>(m2)];
-                if constexpr (m2 != 0) x = cmul_conj(x, tw[(m2 * k1) & (M - 1)]);
-                base[m2 * YS] = x;
-            });
-        }
-        __syncthreads();
-        // inverse pass B: for each m2, R1-point inverse over k1 -> y[R2*m1 + m2]
-        for (int idx = tid; idx < R2 * NS; idx += kThreads) {
-            const int sy = idx % NS, m2 = idx / NS;
-            float2 v[R1];
-            float2* base = tile + m2 * YS + sy;
-#pragma unroll
-            for (int i = 0; i < R1; ++i) v[i] = base[(i * R2) * YS];
-            dif<R1, -1>(v);
-            static_for<R1>([&](auto mc) {
-                constexpr int m1 = decltype(mc)::value;
-                base[(m1 * R2) * YS] = v[bitrev<R1>(m1)];
-            });
-        }
-        __syncthreads();
-        // ---------------- drop the overlap rows, rotate by the NCO, store ------------------------
-        const int ld = p.ld;
-        for (int idx = tid; idx < NS * ld; idx += kThreads) {
-            const int r = idx % ld, sy = idx / ld;
-            const int b = sy / CG, c = sy % CG;
-            const int blk = blk0 + b;
-            const int64_t mg = p.mg_begin + (int64_t)blk * ld + r;
-            if (blk < p.nblocks && mg < p.mg_end && c < p.nchan) {
-                const float2 y = tile[(p.vd + r) * YS + sy];
-                const float2 lo = phasor_f32(nco_phase(p.phase, c, p.w[c], mg * (int64_t)D));
-                p.out[(size_t)c * p.out_stride + (mg - p.mg_begin)] = cmul(y, lo);
-            }
-        }
+        inverse_and_store<M, CG>(tile, tw, p, blk0);
         __syncthreads();
     }
 }

@@ -1,0 +1,276 @@
+// Channel-bank kernel, second generation (int16 PCM, M = 512, D % 4 == 0): same math and same
+// output as k_channelize (channelizer.cuh), restructured around what the first ncu capture showed
+// (issue-bound at 41 % issue utilisation, long-scoreboard stalls on G and on spilled registers):
+//
+//  * PCM tiles arrive by TMA (cp.async.bulk.tensor.2d + mbarrier): 4 blocks x 512 rows x 8 branches
+//    of raw int16 frames land in shared memory while the previous tile is in its pass-2 / MAC
+//    phase.  No register prefetch -> no spills; out-of-range rows (stream start, tail) are
+//    zero-filled by the TMA unit, so the kernel has no bounds checks at all.
+//  * The 512-point branch transform is computed as two 256-point transforms (even rows E, odd rows
+//    O) that live in the two halves of packed f32x2 registers: 16-point DIF x 16-point DIF entirely
+//    in FADD2/FMUL2/FFMA2 (fft_pk.cuh), 128-bit shared-memory accesses; the last radix-2 stage
+//    X[k] = E[k] + W^k O[k], X[k+256] = E[k] - W^k O[k] is fused into the MAC phase (4 FFMA).
+//  * int16 -> float conversion only (I2F); the 1/32768 scale is folded into the G table.
+//  * G is fetched two MAC steps ahead (the first two requests of a tile are issued before the barrier).
+//
+// Shared memory: T[256][33] float4 (E.re,O.re,E.im,O.im) 135 168 B | PCM staging 4 x 16 512 B |
+// inverse twiddles 4 KB | pre-broadcast forward twiddles 4 KB | mbarrier.  Block b's PCM rows are
+// stored rotated by b rows so that the four blocks of a warp's 32 slots hit different banks.
+#pragma once
+#include <cuda.h>
+
+#include "channelizer.cuh"
+#include "fft_pk.cuh"
+
+namespace iq2a {
+
+constexpr int kStageRows = 516;                    // 512 + rotation slack, 3 TMA boxes of 172 rows
+constexpr int kBoxRows = 172;
+constexpr int kStageBytes = kStageRows * 32;       // per block: rows of 8 frames x 4 B
+constexpr int kTileBytes2 = 256 * 33 * 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// spectrum slot of thread j in the MAC phase -> DFT bin (must match k_build_g layout 1)
+__host__ __device__ inline int slot_to_bin_v2(int j) {
+    const int r = j & 255;
+    return (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap, const int64_t tmap_row0) {
+    constexpr int BT = kBlocksPerSet, P = 8, RS = 33;
+    constexpr int NS = CG * BT, YS = NS | 1;
+    static_assert(BT == 4 && (size_t)512 * YS * sizeof(float2) <= (size_t)kTileBytes2, "layout");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* T = reinterpret_cast<float4*>(smem_raw);
+    unsigned char* stage = smem_raw + kTileBytes2;
+    float2* tw512 = reinterpret_cast<float2*>(stage + BT * kStageBytes);
+    float4* tw256b = reinterpret_cast<float4*>(tw512 + 512);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw256b + 256);
+
+    const int tid = threadIdx.x;
+    const int slot = tid & 31, rg = tid >> 5;
+    const int b_slot = slot >> 3, pl = slot & 7;
+
+    for (int i = tid; i < 512; i += kThreads) tw512[i] = p.twid[i];
+    for (int i = tid; i < 256; i += kThreads) {
+        const float2 w = p.twid[2 * i];                       // W_256^i = W_512^{2i} = (cos, -sin)
+        tw256b[i] = make_float4(w.x, w.x, w.y, w.y);
+    }
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    const int D = p.decim;
+    const int ntiles = (D + P - 1) / P;
+    const int nsets = (p.nblocks + BT - 1) / BT;
+    uint32_t parity = 0;
+
+    // MAC-phase identity of this thread: row r of T, upper/lower half of the spectrum
+    const int r_mac = tid & 255, hb = tid >> 8;
+    float2 wc;
+    {
+        const int kq = (r_mac >> 4) + 16 * (r_mac & 15);      // bin within the 256-point halves
+        const float2 w = p.twid[kq];                          // W_512^{k'}
+        wc = hb ? make_float2(-w.x, -w.y) : w;
+    }
+    const int kbin = slot_to_bin_v2(tid);
+    const int yrow = (kbin & 31) * 16 + (kbin >> 5);          // slot the inverse transform expects
+    const float2* __restrict__ gp = p.gtab + tid;
+
+    for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
+        const int blk0 = set * BT;
+        float2 acc[CG][BT];
+#pragma unroll
+        for (int c = 0; c < CG; ++c)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[c][b] = make_float2(0.f, 0.f);
+
+        auto issue = [&](int t) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, BT * kStageBytes);
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                const int64_t row0 = p.mg_begin + (int64_t)(blk0 + b) * p.ld - p.vd;
+                const int rt = (int)(row0 - tmap_row0) - b;   // rotation: block b stored b rows lower
+#pragma unroll
+                for (int i = 0; i < kStageRows / kBoxRows; ++i)
+                    tma_load_2d(stage + b * kStageBytes + i * kBoxRows * 32, &tmap, t * P, rt + i * kBoxRows, bar);
+            }
+        };
+        if (tid == 0) issue(0);
+
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            // ------------- pass 1: two 16-point DIFs (even / odd rows) per thread, packed ---------------
+            {
+                const int m2 = rg;
+                const uint32_t* st = reinterpret_cast<const uint32_t*>(stage + b_slot * kStageBytes) + pl;
+                pk_t re[16], im[16];
+#pragma unroll
+                for (int m1 = 0; m1 < 16; ++m1) {
+                    const int row = 32 * m1 + 2 * m2 + b_slot;
+                    uint32_t w0 = st[row * 8], w1 = st[(row + 1) * 8];
+                    if (p.iq_swap) {
+                        w0 = __funnelshift_l(w0, w0, 16);
+                        w1 = __funnelshift_l(w1, w1, 16);
+                    }
+                    // int16 -> float without the (quarter-rate) I2F unit: 0x4B00_0000 | (s ^ 0x8000) is the
+                    // float 8388608 + 32768 + s; the bias comes off with one packed add per E/O pair.
+                    const pk_t ui = pk_make(__uint_as_float((w0 & 0xffffu) ^ 0x4B008000u),
+                                            __uint_as_float((w1 & 0xffffu) ^ 0x4B008000u));
+                    const pk_t uq = pk_make(__uint_as_float(__byte_perm(w0, 0x4B00u, 0x5432) ^ 0x8000u),
+                                            __uint_as_float(__byte_perm(w1, 0x4B00u, 0x5432) ^ 0x8000u));
+                    re[m1] = pk_add(ui, pk_bc(-8421376.0f));
+                    im[m1] = p.q_neg ? pk_sub(pk_bc(8421376.0f), uq) : pk_add(uq, pk_bc(-8421376.0f));
+                }
+                pk_dif<16>(re, im);
+                ulonglong2* dst = reinterpret_cast<ulonglong2*>(T) + m2 * RS + slot;
+                static_for<16>([&](auto kc) {
+                    constexpr int k1 = decltype(kc)::value;
+                    pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
+                    if constexpr (k1 != 0) {
+                        const float4 w = tw256b[(m2 * k1) & 255];           // (wr, wr, wi, wi), W = wr + j wi
+                        const pk_t wr = pk_make(w.x, w.y), wi = pk_make(w.z, w.w);
+                        const pk_t nr = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
+                        const pk_t ni = pk_fma(xr, wi, pk_mul(xi, wr));
+                        xr = nr;
+                        xi = ni;
+                    }
+                    dst[(k1 * 16) * RS] = make_ulonglong2(xr, xi);
+                });
+            }
+            __syncthreads();
+            if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+            // ------------- pass 2: 16-point DIF over m2, in place ----------------------------------------
+            {
+                const int k1 = rg;
+                ulonglong2* base = reinterpret_cast<ulonglong2*>(T) + (k1 * 16) * RS + slot;
+                pk_t re[16], im[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const ulonglong2 v = base[i * RS];
+                    re[i] = v.x;
+                    im[i] = v.y;
+                }
+                pk_dif<16>(re, im);
+                static_for<16>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    base[k2 * RS] = make_ulonglong2(re[bitrev<16>(k2)], im[bitrev<16>(k2)]);
+                });
+            }
+            // G for the first two steps of this tile is requested before the barrier so that the L2 round
+            // trip overlaps the wait; inside the loop the table is fetched two steps ahead.
+            float2 g0[CG], g1[CG];
+            {
+                const int pa = t * P, pb1 = min(t * P + 1, D - 1);
+#pragma unroll
+                for (int c = 0; c < CG; ++c) {
+                    g0[c] = __ldg(gp + ((size_t)pa * CG + c) * 512);
+                    g1[c] = __ldg(gp + ((size_t)pb1 * CG + c) * 512);
+                }
+            }
+            __syncthreads();
+            // ------------- last radix-2 stage fused with the multiply-accumulate --------------------------
+            const float4* trow = T + r_mac * RS;
+            auto mac_step = [&](int q, const float2 (&g)[CG]) {
+#pragma unroll
+                for (int b = 0; b < BT; ++b) {
+                    const float4 v = trow[b * P + q];                    // (E.re, O.re, E.im, O.im)
+                    const float xr = fmaf(wc.x, v.y, fmaf(-wc.y, v.w, v.x));
+                    const float xi = fmaf(wc.x, v.w, fmaf(wc.y, v.y, v.z));
+#pragma unroll
+                    for (int c = 0; c < CG; ++c) {
+                        acc[c][b].x = fmaf(g[c].x, xr, acc[c][b].x);
+                        acc[c][b].x = fmaf(-g[c].y, xi, acc[c][b].x);
+                        acc[c][b].y = fmaf(g[c].x, xi, acc[c][b].y);
+                        acc[c][b].y = fmaf(g[c].y, xr, acc[c][b].y);
+                    }
+                }
+            };
+            auto gload = [&](float2 (&g)[CG], int pb) {
+                const int pn = min(pb, D - 1);
+#pragma unroll
+                for (int c = 0; c < CG; ++c) g[c] = __ldg(gp + ((size_t)pn * CG + c) * 512);
+            };
+            if (t * P + P <= D) {
+                // full tile: statically rotated register sets, no copies
+                float2 g2[CG];
+                static_for<P>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    if constexpr (q % 3 == 0) { gload(g2, t * P + q + 2); mac_step(q, g0); }
+                    else if constexpr (q % 3 == 1) { gload(g0, t * P + q + 2); mac_step(q, g1); }
+                    else { gload(g1, t * P + q + 2); mac_step(q, g2); }
+                });
+            } else {
+                for (int q = 0; q < P && t * P + q < D; ++q) {
+                    float2 g2[CG];
+                    gload(g2, t * P + q + 2);
+                    mac_step(q, g0);
+#pragma unroll
+                    for (int c = 0; c < CG; ++c) {
+                        g0[c] = g1[c];
+                        g1[c] = g2[c];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ------------- output spectra -> shared (layout of the shared inverse), inverse, store -------------
+        float2* ytile = reinterpret_cast<float2*>(T);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int c = 0; c < CG; ++c) ytile[yrow * YS + b * CG + c] = acc[c][b];
+        inverse_and_store<512, CG>(ytile, tw512, p, blk0);
+        __syncthreads();
+    }
+}
+
+constexpr size_t kSmem2 = (size_t)kTileBytes2 + kBlocksPerSet * kStageBytes + 512 * sizeof(float2) + 256 * sizeof(float4) + 16;
+
+template <int CG>
+static int launch_channelize2_cg(const ChannelizeParams& p, const CUtensorMap& tmap, int64_t tmap_row0, int n_sm,
+                                 cudaStream_t st) {
+    auto kern = k_channelize2<CG>;
+    static bool configured = false;
+    if (!configured) {
+        IQ2A_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+        configured = true;
+    }
+    const int nsets = (p.nblocks + kBlocksPerSet - 1) / kBlocksPerSet;
+    const int grid = nsets < n_sm ? nsets : n_sm;
+    kern<<<grid, kThreads, kSmem2, st>>>(p, tmap, tmap_row0);
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
+}  // namespace iq2a

@@ -215,7 +215,8 @@ int launch_head_direct(const HeadParams& p, int codec, int nrows, int nchan, cud
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps, int ntaps, double w, int D,
                                                   int M, int R1, int qn, const double2* __restrict__ wtab,
-                                                  float2* __restrict__ gout, int cg, int c_in_group) {
+                                                  float2* __restrict__ gout, int cg, int c_in_group, int layout,
+                                                  double scale) {
     extern __shared__ double2 s_g[];    // [qn]
     const int p = blockIdx.x;
     for (int q = threadIdx.x; q < qn; q += blockDim.x) {
@@ -230,10 +231,16 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
     }
     __syncthreads();
     const int R2 = M / R1;
-    const double inv_m = 1.0 / (double)M;
+    const double inv_m = scale / (double)M;
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
-        const int k1 = j / R2, k2 = j % R2;
-        const int bin = k1 + R1 * k2;
+        int bin;
+        if (layout == 0) {
+            const int k1 = j / R2, k2 = j % R2;
+            bin = k1 + R1 * k2;
+        } else {
+            const int r = j & 255;
+            bin = (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
+        }
         double ar = 0.0, ai = 0.0;
         for (int q = 0; q < qn; ++q) {
             const double2 t = wtab[(int)(((int64_t)bin * q) % M)];   // exp(-2 pi j bin q / M)
@@ -246,9 +253,10 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
 }
 
 int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int R1, int qn,
-                   const double2* d_wtab, float2* d_gout, int cg, int c_in_group, cudaStream_t st) {
+                   const double2* d_wtab, float2* d_gout, int cg, int c_in_group, int layout, double scale,
+                   cudaStream_t st) {
     k_build_g<<<D, 256, (size_t)qn * sizeof(double2), st>>>(d_taps, ntaps, w, D, M, R1, qn, d_wtab, d_gout, cg,
-                                                            c_in_group);
+                                                            c_in_group, layout, scale);
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }

@@ -25,10 +25,16 @@ int launch_fir_direct(const float2* d_x, int64_t n_out, const double* d_taps, in
                       cudaStream_t st);
 int launch_decimate(const float2* d_x, int64_t start, int factor, int64_t n_out, float2* d_y, cudaStream_t st);
 int launch_head_direct(const HeadParams& p, int codec, int nrows, int nchan, cudaStream_t st);
+// layout 0: slot order of k_channelize (j' = k1*R2 + k2 <-> bin k1 + R1*k2); layout 1: k_channelize2
+// (thread j <-> bin (r>>4) + 16*(r&15) + 256*(j>>8), r = j & 255).  `scale` multiplies the table.
 int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int R1, int qn,
-                   const double2* d_wtab, float2* d_gout, int cg, int c_in_group, cudaStream_t st);
+                   const double2* d_wtab, float2* d_gout, int cg, int c_in_group, int layout, double scale,
+                   cudaStream_t st);
 
 int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, int n_sm, cudaStream_t st);
 int channelize_max_group(int m_fft);
+bool channelize2_available();
+int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
+                       int n_sm, cudaStream_t st);
 
 }  // namespace iq2a

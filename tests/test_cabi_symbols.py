@@ -35,7 +35,7 @@ def test_structs_match_header_layout():
     assert C.sizeof(_lib.ChannelState) == 32
     assert C.sizeof(_lib.BankConfig) == 48
     assert C.sizeof(_lib.ChannelDesc) == 40
-    assert C.sizeof(_lib.BankInfo) == 40
+    assert C.sizeof(_lib.BankInfo) == 48
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -229,6 +229,36 @@ def test_stream_case_e_preview_truncation(gpu):
     _check(*_stream(gpu, "case_e_truncated", ["case_e_truncated"], limit=m["max_input_samples"]))
 
 
+@pytest.mark.parametrize("order", ["iq", "qi_inv"])
+def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
+    """The TMA / packed-f32x2 kernel (generation 2) and the bounds-checked kernel (generation 1)
+    implement the same arithmetic: same capture, ragged call sizes -> same channel samples."""
+    fs, d = 10e6, 104
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    rng = np.random.default_rng(17)
+    n = 700_001
+    raw = rng.integers(-20_000, 20_000, 2 * n, dtype=np.int16)
+    T = gpu["Target"]
+    tg = [T(1.0e6, taps, 1, "iq"), T(-2.2e6, taps, -1, "iq"), T(3.05e6, taps, 1, "iq")]
+    sizes = [300_000, 3, 101, 104, 250_000, n]
+
+    def run():
+        with gpu["ChannelBank"](fs, d, tg, iq_order=order, ref_chunk=1 << 18, fft_size=512) as bank:
+            gen, pos, parts = bank.kernel_generation, 0, []
+            for sz in sizes:
+                e = min(n, pos + sz)
+                if e > pos:
+                    parts.append(bank.process_chunk(raw[2 * pos:2 * e], want_baseband=True).baseband.copy())
+                pos = e
+            return gen, np.concatenate(parts, axis=1)
+    gen2, bb2 = run()
+    monkeypatch.setenv("IQ2A_CHANNELIZER", "v1")
+    gen1, bb1 = run()
+    assert (gen2, gen1) == (2, 1)
+    assert bb1.shape == bb2.shape == (3, orc.decimated_count(0, n, d))
+    assert np.abs(bb1 - bb2).max() <= 1e-6 * 20_000 / 32768 * 4
+
+
 def test_chunk_split_invariance_and_state_roundtrip(gpu):
     """Feeding the same capture in different call sizes gives the same audio (NFM has no per-chunk
     semantics); get_state/set_state moves the carried decoder state between banks."""
