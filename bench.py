@@ -244,11 +244,9 @@ def main() -> None:
     n_seg = (n_seg // chunk) * chunk if n_seg >= chunk else n_seg     # segments start on the reference chunk grid
     d, fs_ch, targets = make_targets()
     bank = ChannelBank(FS, d, targets, codec="pcm_s16le", iq_order="iq", ref_chunk=chunk, device=local_rank)
-    warm_rows = 600 if rank > 0 else 0                               # de-emphasis settles to < 1e-9
-    seg_begin = rank * n_seg
-    seg_end = seg_begin + n_seg
-    first = max(0, seg_begin - bank.halo - (warm_rows + 1) * d)
-    first -= first % 4                                             # 16-byte aligned int16 frames for the TMA path
+    from iq_to_audio_b200 import sharding
+    seg = sharding.plan_segments(world * n_seg, world, chunk, d, bank.halo, ["nfm"] * len(OFFSETS))[rank]
+    warm_rows, seg_begin, seg_end, first = seg.warmup_rows, seg.begin, seg.end, seg.first_frame
     capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
     audio = torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
@@ -306,8 +304,8 @@ def main() -> None:
             nonlocal bytes_out
             bank.reset()
             bytes_out = 0
-            for k in range(nchunks):
-                r = bank.process_chunk(host_np[2 * k * chunk:2 * min((k + 1) * chunk, n_seg)])
+            views = (host_np[2 * k * chunk:2 * min((k + 1) * chunk, n_seg)] for k in range(nchunks))
+            for r in bank.stream(views):
                 bytes_out += r.audio.nbytes + r.clipped.nbytes
         e2e_step()
         sync_all()
@@ -323,7 +321,7 @@ def main() -> None:
             e2e_ms = float(t.item())
         e2e = {"value": world * n_seg / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(4 * n_seg),
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e2e_ms,
-               "api": "ChannelBank.process_chunk per 4 Mi-sample reference chunk, pinned host input"}
+               "api": "ChannelBank.stream: submit/collect per 4 Mi-sample reference chunk, 2 in flight, pinned host input"}
 
     if rank != 0:
         if world > 1:

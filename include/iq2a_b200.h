@@ -131,6 +131,15 @@ int iq2a_bank_process_chunk(iq2a_bank* bank, const void* frames, int64_t n_frame
                             float* audio, float* clipped, float* baseband, int64_t out_stride,
                             int64_t* n_out, double* rms_dbfs);
 
+/* The same step split in two so that two chunks can be in flight: submit queues the host->device copy
+ * (copy stream) and the kernels + device->host copy of the results (compute stream) and returns;
+ * collect waits for the OLDEST submitted chunk and delivers its results.  `frames` must stay valid
+ * until the chunk is collected.  want: bit 0 audio, bit 1 clipped, bit 2 baseband.
+ * Loop: submit(0); for k: submit(k+1); collect(k).  At most two chunks may be in flight. */
+int iq2a_bank_submit_chunk(iq2a_bank* bank, const void* frames, int64_t n_frames, int32_t want);
+int iq2a_bank_collect_chunk(iq2a_bank* bank, float* audio, float* clipped, float* baseband,
+                            int64_t out_stride, int64_t* n_out, double* rms_dbfs);
+
 /*
  * Whole-segment step on data already resident in HBM (bench / time-sharded runs).
  * `dev_frames` holds global sample indices [first_frame, first_frame + n_frames).

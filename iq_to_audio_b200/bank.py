@@ -176,6 +176,39 @@ class ChannelBank:
         k = int(n_out.value)
         return ChunkResult(audio[:, :k], clipped[:, :k], None if bb is None else bb[:, :k], rms, k)
 
+    def stream(self, chunks, *, want_baseband: bool = False, want_audio: bool = True, want_clipped: bool = True):
+        """Pipelined form of `process_chunk` over an iterable of raw PCM chunks: chunk k+1 is
+        submitted (H2D copy queued) before chunk k's results are collected, so the copy of the next
+        chunk overlaps the kernels of the current one.  Yields one `ChunkResult` per chunk, in order."""
+        want = (1 if want_audio else 0) | (2 if want_clipped else 0) | (4 if want_baseband else 0)
+        pending = []          # [(keepalive, n_frames)]
+
+        def collect(n):
+            cap = max(1, (n + self.decimation - 1) // self.decimation + 1)
+            cc = self.n_channels
+            audio = np.empty((cc, cap), dtype=np.float32) if want_audio else None
+            clipped = np.empty((cc, cap), dtype=np.float32) if want_clipped else None
+            bb = np.empty((cc, cap), dtype=np.complex64) if want_baseband else None
+            rms = np.zeros(cc, dtype=np.float64)
+            n_out = C.c_int64(0)
+            _lib.check(self._lib.iq2a_bank_collect_chunk(self._h, _lib.ptr(audio), _lib.ptr(clipped), _lib.ptr(bb), cap,
+                                                         C.byref(n_out), rms.ctypes.data_as(C.POINTER(C.c_double))))
+            k = int(n_out.value)
+            return ChunkResult(None if audio is None else audio[:, :k], None if clipped is None else clipped[:, :k],
+                               None if bb is None else bb[:, :k], rms, k)
+
+        for raw in chunks:
+            addr, n = self.frames_in(raw)
+            keep = self._keep
+            _lib.check(self._lib.iq2a_bank_submit_chunk(self._h, addr, n, want))
+            pending.append((keep, n))
+            if len(pending) == 2:
+                _, n0 = pending.pop(0)
+                yield collect(n0)
+        while pending:
+            _, n0 = pending.pop(0)
+            yield collect(n0)
+
     # -- resident: a whole segment already in HBM --------------------------------------------------
     def process_resident(self, dev_ptr: int, first_frame: int, n_frames: int, seg_begin: int, seg_end: int, *,
                          warmup_rows: int = 0, dev_audio: int | None = None, dev_clipped: int | None = None,

@@ -56,6 +56,40 @@ static int dev_grow(T** p, size_t* cap, size_t need) {
     return IQ2A_OK;
 }
 
+// results of one streamed chunk, in pinned host memory
+struct StreamSlot {
+    int64_t rows = 0, n_frames = 0;
+    int want = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool done_valid = false;
+    float* h_audio = nullptr;
+    float* h_clip = nullptr;
+    float2* h_bb = nullptr;
+    double* h_ss = nullptr;
+    size_t cap = 0;
+    int ensure(size_t nfl, int C) {
+        if (nfl <= cap && h_ss) return 0;
+        release();
+        const size_t want_n = nfl + nfl / 4 + 1024;
+        if (cudaHostAlloc((void**)&h_audio, want_n * sizeof(float), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_clip, want_n * sizeof(float), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_bb, want_n * sizeof(float2), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_ss, (size_t)C * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+            set_error("pinned result buffer allocation failed");
+            return -4;
+        }
+        cap = want_n;
+        return 0;
+    }
+    void release() {
+        if (h_audio) cudaFreeHost(h_audio);
+        if (h_clip) cudaFreeHost(h_clip);
+        if (h_bb) cudaFreeHost(h_bb);
+        if (h_ss) cudaFreeHost(h_ss);
+        h_audio = h_clip = nullptr; h_bb = nullptr; h_ss = nullptr; cap = 0;
+    }
+};
+
 struct Group {
     int first, count;
     size_t g_off;     // offset (float2 elements) into d_gtab
@@ -102,6 +136,10 @@ struct iq2a_bank {
     int ring_cur = 0;
     int64_t ring_frames = 0;        // frames currently held in d_ring[ring_cur] (all before n_pos)
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    StreamSlot slot[2];
+    int64_t submitted = 0, collected = 0;
+    int inflight = 0;
     // optional per-kernel timing (bench.py roofline): CUDA events on the launching stream
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before/after channel bank, after head, after tail
@@ -117,6 +155,12 @@ struct iq2a_bank {
             if (q) cudaFree(q);
         for (cudaEvent_t e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& sl : slot) {
+            sl.release();
+            if (sl.copied) cudaEventDestroy(sl.copied);
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -526,8 +570,12 @@ int iq2a_bank_info_get(const iq2a_bank* b, iq2a_bank_info* info) {
 int iq2a_bank_reset(iq2a_bank* b) {
     if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
     IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    if (b->inflight != 0) { set_error("reset while chunks are in flight"); return IQ2A_ERR_STATE; }
+    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (b->copy_stream) IQ2A_CUDA_TRY(cudaStreamSynchronize(b->copy_stream));
     b->n_pos = 0;
     b->ring_frames = 0;
+    for (auto& sl : b->slot) sl.done_valid = false;
     std::fill(b->phase.begin(), b->phase.end(), 0.0);
     return fresh_state(b);
 }
@@ -598,19 +646,32 @@ int iq2a_bank_copy_gtable(const iq2a_bank* b, float* host_out, int64_t n_complex
     return IQ2A_OK;
 }
 
-int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, float* audio, float* clipped,
-                            float* baseband, int64_t out_stride, int64_t* n_out, double* rms_dbfs) {
+// ---- streaming: two chunks in flight.  submit() queues the H2D copy on the copy stream and the
+// kernels + D2H of the results on the compute stream; collect() waits for the oldest chunk and hands
+// its results over.  H2D of chunk k+1 overlaps the kernels and the D2H of chunk k.
+int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, int32_t want) {
     if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
     if (n_frames < 0 || (n_frames > 0 && !frames)) { set_error("bad frame buffer"); return IQ2A_ERR_INVALID; }
+    if (b->inflight >= 2) { set_error("two chunks already in flight: collect one first"); return IQ2A_ERR_STATE; }
     IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
     const int C = b->C, D = b->D;
     const int fb = frame_bytes(b->cfg.codec);
+    const int si = (int)(b->submitted & 1);
+    StreamSlot& sl = b->slot[si];
+    if (!sl.copied) {
+        IQ2A_CUDA_TRY(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        IQ2A_CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    if (!b->copy_stream) IQ2A_CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     const int64_t mg_begin = ceil_div(b->n_pos, D);
     const int64_t mg_end = ceil_div(b->n_pos + n_frames, D);
     const int64_t rows = mg_end - mg_begin;
-    if (n_out) *n_out = rows;
+    sl.rows = rows;
+    sl.n_frames = n_frames;
+    sl.want = want;
+    b->submitted++;
+    b->inflight++;
     if (n_frames == 0) return IQ2A_OK;                 // every stage returns its (empty) input
-    if (rows > out_stride && (audio || clipped || baseband)) { set_error("output stride %lld < %lld rows", (long long)out_stride, (long long)rows); return IQ2A_ERR_INVALID; }
 
     // stream buffer: [history | new chunk]; history = the (vd+1)*D frames before n_pos
     const int64_t want_hist = std::min<int64_t>((int64_t)(b->vd + 1) * D, b->n_pos);
@@ -618,20 +679,39 @@ int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, 
     // first ring frame on a 4-frame boundary of the global index (16 B for int16 -> TMA-addressable)
     keep = std::max<int64_t>(0, b->n_pos - (((b->n_pos - keep) + 3) & ~(int64_t)3));
     const int nxt = b->ring_cur ^ 1;
+    // the buffer about to be overwritten was read by the chunk before the previous one
+    StreamSlot& prev2 = b->slot[si];   // same parity == chunk k-2, already collected (inflight < 2) -> its kernels are done
+    (void)prev2;
+    // the chunk still in flight (k-1) reads ring[ring_cur]; we only read its tail (history) -> no hazard
     // D extra frames after the chunk: the bulk kernel reads whole rows of D frames (values beyond the
     // data only ever meet zero taps, but must be readable)
-    int rc = dev_grow(&b->d_ring[nxt], &b->ring_cap[nxt], (size_t)(keep + n_frames + D) * fb + 16);
+    const size_t need_bytes = (size_t)(keep + n_frames + D) * fb + 16;
+    if (need_bytes > b->ring_cap[nxt]) {
+        // growing frees the old buffer: make sure nothing queued still uses it
+        IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+        IQ2A_CUDA_TRY(cudaStreamSynchronize(b->copy_stream));
+    }
+    int rc = dev_grow(&b->d_ring[nxt], &b->ring_cap[nxt], need_bytes);
     if (rc) return rc;
+    // ring[nxt] was last read by chunk k-2's kernels: order the copy stream after them
+    if (b->slot[si].done_valid) IQ2A_CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->slot[si].done, 0));
     if (keep > 0)
         IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_ring[nxt], b->d_ring[b->ring_cur] + (size_t)(b->ring_frames - keep) * fb,
-                                      (size_t)keep * fb, cudaMemcpyDeviceToDevice, b->stream));
+                                      (size_t)keep * fb, cudaMemcpyDeviceToDevice, b->copy_stream));
     IQ2A_CUDA_TRY(cudaMemcpyAsync(b->d_ring[nxt] + (size_t)keep * fb, frames, (size_t)n_frames * fb,
-                                  cudaMemcpyHostToDevice, b->stream));
+                                  cudaMemcpyHostToDevice, b->copy_stream));
+    // the row of slack after the data only ever meets zero taps, but in floating point a stale value
+    // would still leave a rounding-level trace in the last block: keep it zero -> bit-reproducible
+    IQ2A_CUDA_TRY(cudaMemsetAsync(b->d_ring[nxt] + (size_t)(keep + n_frames) * fb, 0, (size_t)D * fb, b->copy_stream));
+    IQ2A_CUDA_TRY(cudaEventRecord(sl.copied, b->copy_stream));
+    IQ2A_CUDA_TRY(cudaStreamWaitEvent(b->stream, sl.copied, 0));
     b->ring_cur = nxt;
     b->ring_frames = keep + n_frames;
 
-    if ((rc = dev_grow(&b->d_audio, &b->audio_cap, (size_t)C * std::max<int64_t>(rows, 1)))) return rc;
-    if ((rc = dev_grow(&b->d_clip, &b->clip_cap, (size_t)C * std::max<int64_t>(rows, 1)))) return rc;
+    const size_t r1 = (size_t)std::max<int64_t>(rows, 1);
+    if (C * r1 > b->audio_cap || C * r1 > b->clip_cap) IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if ((rc = dev_grow(&b->d_audio, &b->audio_cap, C * r1))) return rc;
+    if ((rc = dev_grow(&b->d_clip, &b->clip_cap, C * r1))) return rc;
 
     CoreArgs a{};
     a.d_raw = b->d_ring[nxt];
@@ -650,7 +730,7 @@ int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, 
     a.d_audio = b->d_audio;
     a.d_clip = b->d_clip;
     a.d_bb_out = nullptr;
-    a.out_stride = std::max<int64_t>(rows, 1);
+    a.out_stride = (int64_t)r1;
     a.st = b->stream;
     if (rows > 0 && (rc = run_core(b, a))) return rc;
 
@@ -659,28 +739,64 @@ int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, 
     b->n_pos += n_frames;
 
     if (rows > 0) {
-        if (audio)
-            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(audio, out_stride * sizeof(float), b->d_audio, rows * sizeof(float),
-                                            rows * sizeof(float), C, cudaMemcpyDeviceToHost, b->stream));
-        if (clipped)
-            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(clipped, out_stride * sizeof(float), b->d_clip, rows * sizeof(float),
-                                            rows * sizeof(float), C, cudaMemcpyDeviceToHost, b->stream));
-        if (baseband) {
+        // results -> pinned slot buffers (D2H on the compute stream, behind the kernels)
+        const size_t nfl = (size_t)C * rows;
+        if ((rc = sl.ensure(nfl, C))) return rc;
+        if (want & 1)
+            IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_audio, b->d_audio, nfl * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+        if (want & 2)
+            IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_clip, b->d_clip, nfl * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+        if (want & 4) {
             const int64_t stride = (rows + 63) & ~(int64_t)63;
-            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(baseband, out_stride * sizeof(float2), b->d_bb, stride * sizeof(float2),
+            IQ2A_CUDA_TRY(cudaMemcpy2DAsync(sl.h_bb, rows * sizeof(float2), b->d_bb, stride * sizeof(float2),
                                             rows * sizeof(float2), C, cudaMemcpyDeviceToHost, b->stream));
         }
+        IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_ss, b->d_sumsq, C * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     }
-    std::vector<double> ss(C, 0.0);
-    if (rms_dbfs && rows > 0)
-        IQ2A_CUDA_TRY(cudaMemcpyAsync(ss.data(), b->d_sumsq, C * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    IQ2A_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    IQ2A_CUDA_TRY(cudaEventRecord(sl.done, b->stream));
+    sl.done_valid = true;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_collect_chunk(iq2a_bank* b, float* audio, float* clipped, float* baseband, int64_t out_stride,
+                            int64_t* n_out, double* rms_dbfs) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (b->inflight <= 0) { set_error("no chunk in flight"); return IQ2A_ERR_STATE; }
+    IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
+    StreamSlot& sl = b->slot[(int)(b->collected & 1)];
+    b->collected++;
+    b->inflight--;
+    const int C = b->C;
+    const int64_t rows = sl.rows;
+    if (n_out) *n_out = rows;
+    if (sl.n_frames == 0) return IQ2A_OK;
+    if (rows > out_stride && (audio || clipped || baseband)) { set_error("output stride %lld < %lld rows", (long long)out_stride, (long long)rows); return IQ2A_ERR_INVALID; }
+    IQ2A_CUDA_TRY(cudaEventSynchronize(sl.done));
     collect_timing(b);
+    if (rows > 0) {
+        for (int c = 0; c < C; ++c) {
+            if (audio && (sl.want & 1)) std::memcpy(audio + (size_t)c * out_stride, sl.h_audio + (size_t)c * rows, rows * sizeof(float));
+            if (clipped && (sl.want & 2)) std::memcpy(clipped + (size_t)c * out_stride, sl.h_clip + (size_t)c * rows, rows * sizeof(float));
+            if (baseband && (sl.want & 4)) std::memcpy(baseband + 2 * (size_t)c * out_stride, sl.h_bb + (size_t)c * rows, rows * sizeof(float2));
+        }
+    }
     if (rms_dbfs) {
         std::vector<int64_t> cnt(C, rows);
+        std::vector<double> ss(C, 0.0);
+        if (rows > 0) std::memcpy(ss.data(), sl.h_ss, C * sizeof(double));
         stats_to_dbfs(ss.data(), cnt.data(), C, rms_dbfs);
     }
     return IQ2A_OK;
+}
+
+int iq2a_bank_process_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, float* audio, float* clipped,
+                            float* baseband, int64_t out_stride, int64_t* n_out, double* rms_dbfs) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (b->inflight != 0) { set_error("process_chunk while submitted chunks are in flight"); return IQ2A_ERR_STATE; }
+    const int want = (audio ? 1 : 0) | (clipped ? 2 : 0) | (baseband ? 4 : 0);
+    int rc = iq2a_bank_submit_chunk(b, frames, n_frames, want);
+    if (rc) { if (b->inflight > 0) { b->inflight--; b->collected++; } return rc; }
+    return iq2a_bank_collect_chunk(b, audio, clipped, baseband, out_stride, n_out, rms_dbfs);
 }
 
 static int resident_common(iq2a_bank* b, const void* dev_frames, int64_t first_frame, int64_t n_frames,

@@ -1,0 +1,551 @@
+"""Host pipeline for the B200 path: the reference's `ProcessingPipeline.run` loop body
+(``src/iq_to_audio/processing.py:741-1211``) driving a `ChannelBank` instead of the per-target
+numpy stage objects.
+
+What is kept from the reference surface: `ProcessingConfig` field names, `ProcessingPipeline(config)
+.run(progress_sink) -> ProcessingResult`, `.cancel()`, `ProcessingCancelled`, `IQReader`,
+`AudioWriter`, the decimation / chunk / filter / mix-sign derivations, per-chunk cancel polling and
+progress calls, preview truncation (`max_input_seconds`), removal of a cancelled run's output.
+What is new: `ProcessingConfig.target_freqs` -- several targets run as ONE pass over the capture
+(the reference runs them as sequential passes, ``cli.py:683-710``), and the capture is read as raw
+PCM bytes (the sample-format conversion and IQ order fix happen on the GPU), so the decode-side
+ffmpeg subprocess is not needed for WAV/raw inputs.  The encode side is unchanged: float32 audio is
+piped to ffmpeg for the 48 kHz resample + PCM_16 encode when ffmpeg is available.
+
+Out of scope here: metadata sniffing via ffprobe/soundfile, stage plots,
+pass-through slice writers, the GUI.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import queue
+import re
+import shutil
+import struct
+import subprocess
+import threading
+import wave
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib
+from .bank import ChannelBank, Target
+from .processing import channel_decimation, choose_mix_sign, design_channel_filter, tune_chunk_size
+
+LOG = logging.getLogger(__name__)
+
+FFMPEG_HINT = ("ffmpeg executable not found. Install FFmpeg and ensure it is on PATH "
+               "(or point IQ_TO_AUDIO_FFMPEG at it).")
+
+_CODEC_BY_FORMAT = {"wav-s16": ("wav", "pcm_s16le"), "wav-u8": ("wav", "pcm_u8"), "wav-f32": ("wav", "pcm_f32le"),
+                    "raw-cs16": ("raw", "pcm_s16le"), "raw-cu8": ("raw", "pcm_u8"), "raw-cf32": ("raw", "pcm_f32le"),
+                    "pcm_s16le": (None, "pcm_s16le"), "pcm_u8": (None, "pcm_u8"), "pcm_f32le": (None, "pcm_f32le")}
+_RAW_SUFFIX = {".cu8": "pcm_u8", ".cs16": "pcm_s16le", ".cf32": "pcm_f32le", ".iq": "pcm_s16le"}
+_FRAME_BYTES = {"pcm_u8": 2, "pcm_s16le": 4, "pcm_f32le": 8}
+
+
+@dataclass
+class ProcessingConfig:
+    """Same fields as the reference's ProcessingConfig (processing.py:38-62) plus `target_freqs`."""
+    in_path: Path
+    target_freq: float = 0.0
+    bandwidth: float = 12_500.0
+    center_freq: float | None = None
+    center_freq_source: str | None = None
+    demod_mode: str = "nfm"
+    fs_ch_target: float = 96_000.0
+    deemph_us: float = 300.0
+    agc_enabled: bool = True
+    output_path: Path | None = None
+    dump_iq_path: Path | None = None
+    chunk_size: int = 1_048_576
+    filter_block: int = 65_536
+    iq_order: str = "iq"
+    probe_only: bool = False
+    mix_sign_override: int | None = None
+    plot_stages_path: Path | None = None
+    fft_workers: int | None = None
+    max_input_seconds: float | None = None
+    input_container: str | None = None
+    input_format: str | None = None
+    input_format_source: str | None = None
+    input_sample_rate: float | None = None
+    target_freqs: list[float] | None = None      # extension: batch of targets in one pass
+    device: int = 0
+
+
+@dataclass
+class SampleRateProbe:
+    ffprobe: float | None = None
+    header: float | None = None
+    wave: float | None = None
+
+    @property
+    def value(self) -> float:
+        for v in (self.wave, self.header, self.ffprobe):
+            if v:
+                return float(v)
+        raise RuntimeError("sample rate unavailable")
+
+
+@dataclass
+class ProcessingResult:
+    sample_rate_probe: SampleRateProbe
+    center_freq: float
+    target_freq: float
+    freq_offset: float
+    decimation: int
+    fs_channel: float
+    mix_sign: int
+    audio_peak: float
+    output_path: Path | None = None
+    samples_processed: int = 0
+
+
+class ProcessingCancelled(RuntimeError):  # noqa: N818
+    """Raised when processing is aborted early by user request."""
+
+
+# ------------------------------------------------------------------------------------------
+# input: raw PCM frames straight from the container
+# ------------------------------------------------------------------------------------------
+@dataclass
+class InputFormat:
+    container: str      # "wav" | "raw"
+    codec: str          # pcm_u8 | pcm_s16le | pcm_f32le
+    sample_rate: float | None
+    data_offset: int
+
+    @property
+    def bytes_per_frame(self) -> int:
+        return _FRAME_BYTES[self.codec]
+
+
+def _scan_wav(path: Path) -> InputFormat:
+    """Walk the RIFF chunks up to 'data'.  The data chunk's declared length is ignored and the
+    payload is read to end of file -- what `-ignore_length 1` does for > 4 GiB SDR++ captures
+    (ref: processing.py:149-150)."""
+    with path.open("rb") as fh:
+        head = fh.read(12)
+        if len(head) < 12 or head[:4] not in (b"RIFF", b"RF64") or head[8:12] != b"WAVE":
+            raise ValueError(f"{path} is not a RIFF/WAVE file")
+        codec, rate, channels = None, None, None
+        while True:
+            hdr = fh.read(8)
+            if len(hdr) < 8:
+                raise ValueError(f"{path}: no data chunk")
+            tag, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
+            if tag == b"fmt ":
+                body = fh.read(size + (size & 1))
+                fmt, channels, rate, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+                if fmt == 0xFFFE and len(body) >= 26:
+                    fmt = struct.unpack("<H", body[24:26])[0]
+                codec = {(1, 8): "pcm_u8", (1, 16): "pcm_s16le", (3, 32): "pcm_f32le"}.get((fmt, bits))
+                if codec is None:
+                    raise ValueError(f"{path}: unsupported WAV encoding (format {fmt}, {bits} bits)")
+            elif tag == b"data":
+                if codec is None:
+                    raise ValueError(f"{path}: data chunk before fmt chunk")
+                if channels != 2:
+                    raise ValueError(f"{path}: expected a 2-channel (I/Q) capture, found {channels} channels")
+                return InputFormat("wav", codec, float(rate), fh.tell())
+            else:
+                fh.seek(size + (size & 1), os.SEEK_CUR)
+
+
+def resolve_input(path: Path, requested: str | None, container_hint: str | None,
+                  sample_rate: float | None) -> InputFormat:
+    container, codec = container_hint, None
+    if requested:
+        key = requested.lower()
+        if key not in _CODEC_BY_FORMAT:
+            raise ValueError(f"Unsupported input format '{requested}'")
+        c, codec = _CODEC_BY_FORMAT[key]
+        container = c or container
+    suffix = path.suffix.lower()
+    if container is None:
+        container = "raw" if suffix in _RAW_SUFFIX else "wav"
+    if container == "raw":
+        return InputFormat("raw", codec or _RAW_SUFFIX.get(suffix, "pcm_s16le"), sample_rate, 0)
+    fmt = _scan_wav(path)
+    if codec:
+        fmt.codec = codec
+    return fmt
+
+
+class IQReader:
+    """Stream a baseband capture in chunks of `chunk_size` complex samples (ref: processing.py:84-279).
+
+    `read_raw_block()` returns the PCM payload bytes of the next chunk (what the fused path eats);
+    iterating yields complex64 blocks with the IQ order applied, like the reference, by running the
+    unpack kernel with a zero-frequency oscillator."""
+
+    def __init__(self, path: Path, chunk_size: int, iq_order: str, input_format: InputFormat, *,
+                 sample_rate: float | None = None):
+        if iq_order not in _lib.ORDER_IDS:
+            raise ValueError(f"Unsupported iq_order '{iq_order}'")
+        self.path = Path(path)
+        self.chunk_size = int(chunk_size)
+        self.iq_order = iq_order
+        self.input_format = input_format
+        self.sample_rate = sample_rate
+        self.input_bytes_per_frame = input_format.bytes_per_frame
+        self._fh = None
+
+    def __enter__(self) -> "IQReader":
+        if self.input_format.container == "raw" and not (self.sample_rate and self.sample_rate > 0):
+            raise ValueError("Raw IQ inputs require a sample rate override. Provide --input-sample-rate.")
+        self._fh = self.path.open("rb", buffering=0)
+        self._fh.seek(self.input_format.data_offset)
+        return self
+
+    def __exit__(self, *exc) -> None:
+        if self._fh:
+            self._fh.close()
+            self._fh = None
+
+    def read_raw_block(self, max_frames: int | None = None) -> np.ndarray | None:
+        if self._fh is None:
+            raise RuntimeError("IQReader has not been entered.")
+        frames = self.chunk_size if max_frames is None else min(self.chunk_size, max_frames)
+        fb = self.input_bytes_per_frame
+        buf = np.empty(frames * fb, dtype=np.uint8)
+        got = self._fh.readinto(memoryview(buf))
+        while 0 < got < buf.size:
+            more = self._fh.readinto(memoryview(buf)[got:])
+            if not more:
+                break
+            got += more
+        got -= got % fb                      # drop a trailing partial frame (ref: processing.py:253-256)
+        return buf[:got] if got > 0 else None
+
+    def __iter__(self):
+        lib = _lib.load()
+        codec_id = _lib.CODEC_IDS[self.input_format.codec]
+        while True:
+            raw = self.read_raw_block()
+            if raw is None:
+                break
+            n = raw.size // self.input_bytes_per_frame
+            out = np.empty(n, dtype=np.complex64)
+            _lib.check(lib.iq2a_unpack_mix(raw.ctypes.data, n, codec_id, _lib.ORDER_IDS[self.iq_order], 0.0, 0.0,
+                                           out.ctypes.data, 0))
+            yield out
+
+
+# ------------------------------------------------------------------------------------------
+# output: float32 audio -> 48 kHz PCM_16 WAV
+# ------------------------------------------------------------------------------------------
+def resolve_ffmpeg_executable() -> Path | None:
+    override = os.environ.get("IQ_TO_AUDIO_FFMPEG")        # ref: utils.py:126-151
+    if override:
+        p = Path(override)
+        return p if p.exists() else None
+    found = shutil.which("ffmpeg")
+    return Path(found) if found else None
+
+
+class AudioWriter:
+    """ref: processing.py:381-524.  `write()` takes decoder output (computes peak + clip like the
+    reference); `write_clipped()` takes audio the GPU already clipped.  With ffmpeg present the
+    float32 stream is piped to it exactly as the reference does (`-f f32le -ar round(fs) ... -acodec
+    pcm_s16le -ar 48000`).  Without ffmpeg the writer falls back to a plain PCM_16 WAV at the channel
+    rate (no resampling) and says so -- the 48 kHz libswresample-exact stage is the next row of the
+    scope table, not part of this one."""
+
+    def __init__(self, output_path: Path, input_rate: float, *, require_ffmpeg: bool = False):
+        self.output_path = Path(output_path)
+        self.input_rate = float(input_rate)
+        self.ffmpeg_rate = max(1, int(round(self.input_rate)))
+        self.peak = 0.0
+        self._closed = False
+        self._error: BaseException | None = None
+        self.proc = None
+        self._wav = None
+        ffmpeg = resolve_ffmpeg_executable()
+        if ffmpeg is None and require_ffmpeg:
+            raise RuntimeError(FFMPEG_HINT)
+        self.output_path.parent.mkdir(parents=True, exist_ok=True)
+        if ffmpeg is not None:
+            cmd = [str(ffmpeg), "-hide_banner", "-loglevel", "error", "-y", "-f", "f32le", "-ac", "1", "-ar",
+                   str(self.ffmpeg_rate), "-i", "-", "-acodec", "pcm_s16le", "-ar", "48000", str(self.output_path)]
+            try:
+                self.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stderr=subprocess.PIPE)
+            except OSError as exc:
+                raise RuntimeError(f"Failed to launch ffmpeg: {exc}") from exc
+            self._queue: queue.SimpleQueue = queue.SimpleQueue()
+            self._thread = threading.Thread(target=self._drain, name="AudioWriter", daemon=True)
+            self._thread.start()
+        else:
+            LOG.warning("ffmpeg not found: writing %d Hz PCM_16 without the 48 kHz resample.", self.ffmpeg_rate)
+            self._wav = wave.open(str(self.output_path), "wb")
+            self._wav.setnchannels(1)
+            self._wav.setsampwidth(2)
+            self._wav.setframerate(self.ffmpeg_rate)
+
+    def _drain(self) -> None:
+        pipe = self.proc.stdin
+        try:
+            while True:
+                item = self._queue.get()
+                if item is None:
+                    break
+                pipe.write(item)
+        except BaseException as exc:  # broken pipe etc.: surfaced on the next write/close
+            self._error = exc
+
+    def write(self, samples: np.ndarray) -> None:
+        if samples.size == 0:
+            return
+        pk = float(np.max(np.abs(samples)))
+        self.peak = max(self.peak, pk)
+        self.write_clipped(np.clip(samples, -0.99, 0.99).astype(np.float32, copy=False))
+
+    def write_clipped(self, safe: np.ndarray) -> None:
+        if self._closed:
+            raise RuntimeError("AudioWriter has already been closed.")
+        if self._error:
+            raise RuntimeError("ffmpeg writer failed") from self._error
+        if safe.size == 0:
+            return
+        if self.proc is not None:
+            self._queue.put(np.ascontiguousarray(safe, dtype=np.float32).tobytes())
+        else:
+            pcm = np.clip(np.rint(safe.astype(np.float64) * 32768.0), -32768, 32767).astype("<i2")
+            self._wav.writeframes(pcm.tobytes())
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        if self.proc is not None:
+            self._queue.put(None)
+            self._thread.join(timeout=30)
+            try:
+                self.proc.stdin.close()
+            except OSError:
+                pass
+            try:
+                self.proc.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                self.proc.terminate()
+            if self._error:
+                raise RuntimeError("ffmpeg writer failed") from self._error
+        elif self._wav is not None:
+            self._wav.close()
+
+
+# ------------------------------------------------------------------------------------------
+_FREQ_IN_NAME = re.compile(r"(?<![0-9.])(\d{5,11})\s*hz", re.IGNORECASE)
+
+
+def center_frequency_from_filename(path: Path) -> float | None:
+    """SDR++ names captures `baseband_<freq>Hz_<time>.wav`; the benchmark uses `..._fc-<freq>Hz.wav`."""
+    hits = _FREQ_IN_NAME.findall(Path(path).name)
+    return float(hits[0]) if hits else None
+
+
+class _Progress:
+    """Duck-typed bridge to the reference's ProgressSink (progress.py:26-53): phases ingest /
+    channel / demod / encode advanced once per chunk, status text, cancel callback."""
+
+    def __init__(self, sink, totals: dict[str, float]):
+        self.sink = sink
+        self.done = {k: 0.0 for k in totals}
+        self.totals = totals
+        if sink is not None and hasattr(sink, "start"):
+            try:
+                from types import SimpleNamespace
+                self.phases = {k: SimpleNamespace(key=k, label=k, total=v, unit="samples", completed=0.0)
+                               for k, v in totals.items()}
+                sink.start(list(self.phases.values()), overall_total=float(sum(totals.values())))
+            except TypeError:
+                self.phases = {}
+
+    def advance(self, key: str, amount: float) -> None:
+        if self.sink is None or key not in self.done:
+            return
+        self.done[key] += amount
+        ph = getattr(self, "phases", {}).get(key)
+        if ph is not None and hasattr(self.sink, "advance"):
+            ph.completed = self.done[key]
+            self.sink.advance(ph, amount, overall_completed=float(sum(self.done.values())),
+                              overall_total=float(sum(self.totals.values())))
+
+    def status(self, msg: str) -> None:
+        if self.sink is not None and hasattr(self.sink, "status"):
+            self.sink.status(msg)
+
+    def close(self) -> None:
+        if self.sink is not None and hasattr(self.sink, "close"):
+            self.sink.close()
+
+
+class ProcessingPipeline:
+    def __init__(self, config: ProcessingConfig):
+        self.config = config
+        self._cancelled = False
+
+    def cancel(self) -> None:
+        self._cancelled = True
+
+    def _check_cancel(self, where: str) -> None:
+        if self._cancelled:
+            raise ProcessingCancelled(f"Processing cancelled during {where}.")
+
+    # reference: processing.py:1214-1233
+    def _default_output_path(self, freq: float) -> Path:
+        return self.config.in_path.with_name(f"audio_{int(freq)}_48k.wav")
+
+    def _output_for(self, freq: float, total: int) -> Path:
+        base = self.config.output_path
+        if base is None:
+            return self._default_output_path(freq)
+        if total <= 1:
+            return Path(base)
+        return Path(base).with_name(f"{Path(base).stem}_{int(round(freq))}{Path(base).suffix}")   # cli.py:523-527
+
+    def run(self, progress_sink=None) -> ProcessingResult:
+        return self.run_many(progress_sink)[0]
+
+    def run_many(self, progress_sink=None) -> list[ProcessingResult]:
+        cfg = self.config
+        if hasattr(progress_sink, "set_cancel_callback"):
+            progress_sink.set_cancel_callback(self.cancel)
+        manual_rate = cfg.input_sample_rate
+        if manual_rate is not None and manual_rate <= 0:
+            raise ValueError("Input sample rate override must be positive.")
+        fmt = resolve_input(Path(cfg.in_path), cfg.input_format, cfg.input_container, manual_rate)
+        cfg.input_container = cfg.input_container or fmt.container
+        cfg.input_format = cfg.input_format or fmt.codec
+        if fmt.container == "raw" and manual_rate is None:
+            raise ValueError("Raw IQ inputs require --input-sample-rate (CLI) or a manual entry in the GUI.")
+        sample_rate = float(manual_rate) if manual_rate is not None else float(fmt.sample_rate)
+        probe = SampleRateProbe(wave=sample_rate)
+
+        targets = list(cfg.target_freqs) if cfg.target_freqs else [cfg.target_freq]
+        if any(f <= 0 for f in targets) and not cfg.probe_only:
+            raise ValueError("Target frequency must be positive. Provide --ft or use --interactive.")
+        if cfg.bandwidth <= 0:
+            raise ValueError("Bandwidth must be positive.")
+        center = cfg.center_freq
+        if center is None:
+            center = center_frequency_from_filename(Path(cfg.in_path))
+            if center is None:
+                raise ValueError("Center frequency not supplied and could not be determined from metadata or "
+                                 "filename. Use --fc to provide it explicitly.")
+            cfg.center_freq, cfg.center_freq_source = center, "filename"
+
+        decimation, fs_channel = channel_decimation(sample_rate, cfg.fs_ch_target)       # :885-890
+        chunk = tune_chunk_size(sample_rate, cfg.chunk_size)                            # :929
+        max_samples = None
+        if cfg.max_input_seconds is not None and cfg.max_input_seconds > 0:
+            max_samples = max(1, int(math.floor(cfg.max_input_seconds * sample_rate)))  # :842-845
+        taps = design_channel_filter(sample_rate, cfg.bandwidth, decimation)             # :987
+        LOG.info("Input sample rate %.2f Hz; decimation %d -> %.2f Hz; %d-tap channel filter; chunk %d.",
+                 sample_rate, decimation, fs_channel, len(taps), chunk)
+
+        try:
+            payload = max(Path(cfg.in_path).stat().st_size - fmt.data_offset, 0)
+        except OSError:
+            payload = 0
+        total_in = payload / fmt.bytes_per_frame
+        if max_samples is not None:
+            total_in = min(total_in, max_samples) if total_in > 0 else max_samples
+        prog = _Progress(progress_sink, {"ingest": total_in, "channel": total_in / decimation,
+                                         "demod": total_in / decimation,
+                                         "encode": total_in / sample_rate * 48_000.0})
+        outputs = [self._output_for(f, len(targets)) for f in targets]
+        writers: list[AudioWriter] = []
+        dump = None
+        results: list[ProcessingResult] = []
+        processed = 0
+        try:
+            with IQReader(Path(cfg.in_path), chunk, cfg.iq_order, fmt, sample_rate=sample_rate) as reader:
+                self._check_cancel("initialization")
+                first = reader.read_raw_block(max_samples)
+                if first is None:
+                    raise RuntimeError("Input stream produced no samples.")
+                # mixer sign from the warm-up chunk (processing.py:1028-1042)
+                signs = []
+                if cfg.mix_sign_override in (1, -1):
+                    signs = [cfg.mix_sign_override] * len(targets)
+                else:
+                    lib = _lib.load()
+                    nfr = first.size // fmt.bytes_per_frame
+                    warm = np.empty(nfr, dtype=np.complex64)
+                    _lib.check(lib.iq2a_unpack_mix(first.ctypes.data, nfr, _lib.CODEC_IDS[fmt.codec],
+                                                   _lib.ORDER_IDS[cfg.iq_order], 0.0, 0.0, warm.ctypes.data, cfg.device))
+                    signs = [choose_mix_sign(warm, sample_rate, f - center, taps, decimation) for f in targets]
+                LOG.info("Selected mixer sign(s) %s based on warm-up snippet.", signs)
+                self._check_cancel("warm-up")
+                if cfg.probe_only:
+                    prog.advance("ingest", first.size // fmt.bytes_per_frame)
+                    return [ProcessingResult(probe, center, f, f - center, decimation, fs_channel, s, 0.0)
+                            for f, s in zip(targets, signs)]
+
+                bank = ChannelBank(sample_rate, decimation,
+                                   [Target(f - center, taps, s, cfg.demod_mode, cfg.deemph_us, cfg.agc_enabled)
+                                    for f, s in zip(targets, signs)],
+                                   codec=fmt.codec, iq_order=cfg.iq_order, ref_chunk=chunk, device=cfg.device)
+                writers = [AudioWriter(o, fs_channel) for o in outputs]
+                if cfg.dump_iq_path:
+                    dump = Path(cfg.dump_iq_path).open("wb")
+
+                def blocks():
+                    nonlocal processed
+                    blk = first
+                    idx = 0
+                    while blk is not None:
+                        n = blk.size // fmt.bytes_per_frame
+                        self._check_cancel(f"chunk {idx + 1}")
+                        prog.advance("ingest", n)
+                        prog.status(f"Chunk {idx + 1}: channelize + demodulate")
+                        processed += n
+                        yield blk
+                        idx += 1
+                        left = None if max_samples is None else max_samples - processed
+                        if left is not None and left <= 0:
+                            break
+                        blk = reader.read_raw_block(left)
+
+                with bank:
+                    for res in bank.stream(blocks(), want_baseband=dump is not None, want_audio=False):
+                        prog.advance("channel", float(res.count))
+                        if dump is not None:                        # --dump-iq: channelized cf32 (first target)
+                            dump.write(res.baseband[0].tobytes())
+                        prog.advance("demod", float(res.count))
+                        for w, row in zip(writers, res.clipped):
+                            w.write_clipped(row)
+                        self._check_cancel("encode")
+                        prog.advance("encode", res.count / max(fs_channel, 1e-9) * 48_000.0)
+                    peaks = bank.peaks
+            for w, pk in zip(writers, peaks):
+                w.peak = pk
+            for f, s, o, pk in zip(targets, signs, outputs, peaks):
+                LOG.info("Audio peak level %.2f dBFS.", 20.0 * math.log10(max(pk, 1e-6)))
+                results.append(ProcessingResult(probe, center, f, f - center, decimation, fs_channel, s, pk, o, processed))
+            return results
+        except ProcessingCancelled:
+            for w in writers:
+                try:
+                    w.close()
+                except Exception:
+                    pass
+            writers = []
+            for o in outputs:
+                try:
+                    Path(o).unlink(missing_ok=True)          # ref: processing.py:1205-1211
+                except OSError:
+                    LOG.debug("Failed to remove cancelled output %s", o)
+            raise
+        finally:
+            for w in writers:
+                w.close()
+            if dump is not None:
+                dump.close()
+            prog.close()

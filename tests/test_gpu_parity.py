@@ -259,6 +259,29 @@ def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
     assert np.abs(bb1 - bb2).max() <= 1e-6 * 20_000 / 32768 * 4
 
 
+def test_pipelined_stream_equals_synchronous_chunks(gpu):
+    """ChannelBank.stream (two chunks in flight: H2D of chunk k+1 overlaps the kernels of chunk k)
+    returns exactly what the synchronous per-chunk call returns."""
+    m, fs, d, tg, gold = _targets(gpu, "case_b_nfm_10M", [f"case_b_nfm_10M_t{i}" for i in range(5)])
+    raw = _cases.raw_input("case_b_nfm_10M")
+    n = raw.size // 2
+    chunk = 100_000
+    views = [raw[2 * s:2 * min(s + chunk, n)] for s in range(0, n, chunk)]
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=chunk) as bank:
+        sync = [bank.process_chunk(v, want_baseband=True) for v in views]
+        sync = [(r.audio.copy(), r.clipped.copy(), r.baseband.copy(), r.rms_dbfs.copy()) for r in sync]
+        bank.reset()
+        piped = [(r.audio.copy(), r.clipped.copy(), r.baseband.copy(), r.rms_dbfs.copy())
+                 for r in bank.stream(views, want_baseband=True)]
+        with pytest.raises(RuntimeError, match="no chunk in flight"):
+            gpu["lib"].check(bank._lib.iq2a_bank_collect_chunk(bank._h, None, None, None, 0, None, None))
+    assert len(sync) == len(piped) == len(views)
+    for a, b in zip(sync, piped):
+        for x, y in zip(a[:3], b[:3]):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_allclose(a[3], b[3], rtol=0, atol=1e-9)   # float64 atomics: summation order varies
+
+
 def test_chunk_split_invariance_and_state_roundtrip(gpu):
     """Feeding the same capture in different call sizes gives the same audio (NFM has no per-chunk
     semantics); get_state/set_state moves the carried decoder state between banks."""

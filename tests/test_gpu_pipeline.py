@@ -1,0 +1,115 @@
+"""GPU: the host pipeline (reader -> ChannelBank.stream -> writer), `--benchmark`, cancellation."""
+from __future__ import annotations
+
+import wave
+
+import numpy as np
+import pytest
+
+from oracle import iq_oracle as orc
+from tests import _cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_wav(path, raw_i16, rate):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(int(rate))
+        w.writeframes(raw_i16.tobytes())
+
+
+def _read_pcm(path):
+    with wave.open(str(path), "rb") as w:
+        assert w.getnchannels() == 1 and w.getsampwidth() == 2
+        return w.getframerate(), np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+
+
+@pytest.fixture()
+def no_ffmpeg(monkeypatch):
+    # force the native writer (PCM_16 at the channel rate) so the samples can be compared one to one
+    monkeypatch.setenv("IQ_TO_AUDIO_FFMPEG", "/nonexistent/ffmpeg")
+
+
+def test_pipeline_five_targets_one_pass(tmp_path, no_ffmpeg):
+    from iq_to_audio_b200.pipeline import ProcessingConfig, ProcessingPipeline
+    m = _cases.manifest()["case_b_nfm_10M"]
+    cap = tmp_path / "baseband_100000000Hz_capture.wav"
+    _write_wav(cap, _cases.raw_input("case_b_nfm_10M"), m["fs"])
+    fc = 100_000_000.0
+    cfg = ProcessingConfig(in_path=cap, target_freqs=[fc + t["f_off"] for t in m["targets"]], target_freq=fc,
+                           chunk_size=m["chunk"], mix_sign_override=1, output_path=tmp_path / "out.wav")
+    # chunk_size is only a lower bound (tune_chunk_size): 10 MS/s -> 4 Mi, i.e. the whole test capture is one chunk
+    res = ProcessingPipeline(cfg).run_many()
+    assert len(res) == 5 and cfg.center_freq == fc and cfg.center_freq_source == "filename"
+    for i, r in enumerate(res):
+        g = _cases.load(f"case_b_nfm_10M_t{i}")
+        assert r.decimation == 104 and r.mix_sign == 1 and r.output_path.name == f"out_{int(round(r.target_freq))}.wav"
+        rate, pcm = _read_pcm(r.output_path)
+        assert rate == 96_154 and pcm.size == g["audio"].size                     # ref processing.py:391
+        want = np.clip(np.rint(g["clipped"].astype(np.float64) * 32768.0), -32768, 32767)
+        assert np.abs(pcm.astype(np.int64) - want).max() <= 1                     # +-1 LSB
+        assert abs(r.audio_peak - float(g["peak"])) <= 1e-5
+
+
+def test_pipeline_auto_mix_sign_and_preview(tmp_path, no_ffmpeg):
+    from iq_to_audio_b200.pipeline import ProcessingConfig, ProcessingPipeline
+    cap = tmp_path / "bench_fc-400000000Hz.wav"
+    _write_wav(cap, _cases.raw_input("case_a_nfm_2p5M"), 2.5e6)
+    cfg = ProcessingConfig(in_path=cap, target_freq=400_025_000.0, max_input_seconds=0.06, output_path=tmp_path / "a.wav")
+    r = ProcessingPipeline(cfg).run()
+    g = _cases.load("case_a_nfm_2p5M")
+    assert r.mix_sign == int(g["mix_sign"]) and r.decimation == 26
+    assert r.samples_processed == 150_000
+    rate, pcm = _read_pcm(tmp_path / "a.wav")
+    assert pcm.size == orc.decimated_count(0, 150_000, 26)
+    # the reference tunes the chunk to 1 Mi at 2.5 MS/s: the 150 000-sample preview is one chunk, NFM has no
+    # per-chunk semantics, so the first samples equal the golden stream's
+    want = np.clip(np.rint(g["clipped"][:pcm.size].astype(np.float64) * 32768.0), -32768, 32767)
+    assert np.abs(pcm.astype(np.int64) - want).max() <= 1
+
+
+def test_pipeline_cancel_removes_output(tmp_path, no_ffmpeg):
+    from iq_to_audio_b200.pipeline import ProcessingCancelled, ProcessingConfig, ProcessingPipeline
+    cap = tmp_path / "x_fc-400000000Hz.wav"
+    _write_wav(cap, _cases.raw_input("case_a_nfm_2p5M"), 2.5e6)
+    cfg = ProcessingConfig(in_path=cap, target_freq=400_025_000.0, output_path=tmp_path / "c.wav", mix_sign_override=1)
+    pipe = ProcessingPipeline(cfg)
+
+    class CancelOnFirstAdvance:                      # ref tests/test_processing.py:98-151 (_AutoCancelSink)
+        def start(self, phases, *, overall_total): pass
+        def advance(self, phase, delta, *, overall_completed, overall_total): pipe.cancel()
+        def status(self, message): pass
+        def close(self): pass
+    with pytest.raises(ProcessingCancelled):
+        pipe.run(CancelOnFirstAdvance())
+    assert not (tmp_path / "c.wav").exists()
+
+
+def test_cli_benchmark_surface(no_ffmpeg, caplog):
+    from iq_to_audio_b200 import cli
+    import logging
+    with caplog.at_level(logging.INFO):
+        rc = cli.main(["--benchmark", "--benchmark-seconds", "0.5"])
+    assert rc == 0
+    assert any("Benchmark processed 1250000 IQ samples" in r.getMessage() for r in caplog.records)
+    assert cli.main(["--benchmark", "--benchmark-offset", "2000000"]) == 1        # offset beyond fs/2 -> error exit
+    with pytest.raises(SystemExit):
+        cli.main(["--ft", "1", "--ft", "2", "--ft", "3", "--ft", "4", "--ft", "5", "--ft", "6", "--in", "x.wav"])
+
+
+def test_pipeline_errors(tmp_path, no_ffmpeg):
+    from iq_to_audio_b200.pipeline import ProcessingConfig, ProcessingPipeline
+    cap = tmp_path / "nofreq.wav"
+    _write_wav(cap, _cases.raw_input("case_a_nfm_2p5M")[:20_000], 2.5e6)
+    with pytest.raises(ValueError, match="Center frequency"):
+        ProcessingPipeline(ProcessingConfig(in_path=cap, target_freq=1e6)).run()
+    with pytest.raises(ValueError, match="Target frequency must be positive"):
+        ProcessingPipeline(ProcessingConfig(in_path=cap, center_freq=1e6)).run()
+    raw = tmp_path / "cap.cs16"
+    raw.write_bytes(_cases.raw_input("case_a_nfm_2p5M")[:20_000].tobytes())
+    with pytest.raises(ValueError, match="input-sample-rate"):
+        ProcessingPipeline(ProcessingConfig(in_path=raw, target_freq=1.0e6 + 25e3, center_freq=1e6)).run()
+    r = ProcessingPipeline(ProcessingConfig(in_path=raw, target_freq=1.0e6 + 25e3, center_freq=1e6,
+                                            input_sample_rate=2.5e6, output_path=tmp_path / "r.wav",
+                                            mix_sign_override=1)).run()
+    assert r.samples_processed == 10_000

@@ -1,0 +1,99 @@
+"""CPU-only, world_size 2 over gloo: the time-segment sharding logic (segment plan, halo,
+warm-up, gather order) with the CPU oracle standing in for the per-rank engine."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from iq_to_audio_b200 import sharding
+from oracle import iq_oracle as orc
+from tests import _cases
+
+
+def test_segment_plan_covers_capture_on_the_chunk_grid():
+    segs = sharding.plan_segments(10_000_000, 4, 262_144, 104, 6_552, ["nfm"] * 5)
+    assert segs[0].begin == 0 and segs[-1].end == 10_000_000
+    for a, b in zip(segs, segs[1:]):
+        assert a.end == b.begin and b.begin % 262_144 == 0 and a.row_end == b.row_begin
+    assert segs[0].warmup_rows == 0 and segs[0].first_frame == 0
+    for s in segs[1:]:
+        assert s.warmup_rows == 600 and s.first_frame % 4 == 0
+        assert s.first_frame <= (s.row_begin - 600) * 104 - 6_552
+    assert sum(s.rows for s in segs) == orc.decimated_count(0, 10_000_000, 104)
+    # fewer chunks than ranks -> empty trailing segments, still a partition
+    segs = sharding.plan_segments(300_000, 8, 262_144, 104, 6_552, ["am"])
+    assert sum(s.rows for s in segs) == orc.decimated_count(0, 300_000, 104)
+    assert sharding.warmup_rows_for(["nfm", "usb"]) == 4200
+    with pytest.raises(ValueError):
+        sharding.plan_segments(10, 0, 1, 1, 0, ["nfm"])
+
+
+def _oracle_shard(x, seg, plan, chunk):
+    """What a rank computes: the reference loop started `warmup_rows` early from zero state,
+    with the NCO phase and decimator offset taken from the global index."""
+    d = plan.decimation
+    nt = len(plan.taps)
+    if seg.begin == 0:
+        return orc.run_target(x[: seg.end], plan, chunk).audio
+    h0 = (seg.row_begin - seg.warmup_rows) * d - (nt - 1)
+    nco = orc.NcoState.for_offset(plan.freq_offset, plan.sample_rate)
+    # exact phase at h0: replay the reference's per-chunk wrap up to the chunk holding h0
+    k0 = h0 // chunk
+    for _ in range(k0):
+        nco.phase = orc.nco_advance(nco.phase, nco.increment, plan.mix_sign, chunk)
+    nco.phase = nco.phase + plan.mix_sign * nco.increment * (h0 - k0 * chunk)
+    fir = orc.FirState(plan.taps, plan.filter_block)
+    dec = orc.DecimState(d)
+    dec.offset = h0 % d
+    dem = orc.DemodState.create(plan.mode, plan.fs_channel, deemph_us=plan.deemph_us)
+    # one call per reference chunk piece so that phase wraps happen where the single stream has them
+    audio = []
+    pos = h0
+    while pos < seg.end:
+        nxt = min(seg.end, (pos // chunk + 1) * chunk)
+        mixed = orc.nco_mix(nco, x[pos:nxt], plan.mix_sign)
+        audio.append(orc.demodulate(dem, orc.decimate(dec, orc.fir_overlap_save(fir, mixed)))[0])
+        pos = nxt
+    audio = np.concatenate(audio)
+    return audio[audio.size - seg.rows:]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = _cases.manifest()["case_b_nfm_10M"]
+        x = _cases.complex_input("case_b_nfm_10M")
+        chunk = m["chunk"]
+        plan = orc.TargetPlan(sample_rate=m["fs"], freq_offset=m["targets"][1]["f_off"], mix_sign=1)
+        halo = ((len(plan.taps) - 1 + plan.decimation - 1) // plan.decimation + 1) * plan.decimation
+        segs = sharding.plan_segments(x.size, world, chunk, plan.decimation, halo, ["nfm"])
+        mine = _oracle_shard(x, segs[rank], plan, chunk)
+        local = torch.from_numpy(np.ascontiguousarray(mine)).reshape(1, -1)
+        full = sharding.gather_rows(local, segs, dst=0)
+        peak = sharding.reduce_peak(torch.tensor([float(np.abs(mine).max())]), dst=0)
+        if rank == 0:
+            ret["audio"] = full.numpy()[0].copy()
+            ret["peak"] = float(peak[0])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_time_sharding_reproduces_single_stream():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    g = _cases.load("case_b_nfm_10M_t1")
+    audio = ret["audio"]
+    assert audio.size == g["audio"].size                      # exact row partition, in order
+    assert np.abs(audio - g["audio"]).max() <= 1e-6           # halo + 600-row warm-up: < 1e-8 expected
+    assert abs(ret["peak"] - float(g["peak"])) <= 1e-6
