@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "precise.cuh"
 #include "stage.cuh"
 #include "tail.cuh"
 #include "../../include/iq2a_b200.h"
@@ -104,6 +105,7 @@ struct iq2a_bank {
     int C = 0, D = 1, M = 0, R1 = 32, vd = 0, ld = 0, n_sm = 148;
     bool any_agc = false;
     std::vector<std::vector<double>> taps;
+    std::vector<int64_t> tap_off;   // offsets of each channel's taps in d_taps
     std::vector<int> modes;
     std::vector<double> w;          // signed NCO increments (sign * -2 pi f_off / fs)
     std::vector<double> phase;      // streaming: NCO phase at n_pos per channel
@@ -114,6 +116,11 @@ struct iq2a_bank {
     int64_t launches_v2 = 0;
 
     float2* d_gtab = nullptr;
+    std::vector<int> precise;       // channels on the bit-faithful path (SSB with AGC on)
+    int* d_precise = nullptr;
+    float2* d_mixed = nullptr;   size_t mixed_cap = 0;
+    SeqChunk* d_rec = nullptr;   size_t rec_cap = 0;
+    int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     bool v2_ok = false;
     float2* d_tw = nullptr;
@@ -149,7 +156,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -316,6 +323,38 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         if ((rc = launch_head_direct(h, b->cfg.codec, (int)(last - a.mg_begin), C, a.st))) return rc;
         b->launches++;
     }
+    // ---- bit-faithful channel samples for SSB+AGC channels (precise.cu) ------------------------
+    if (!b->precise.empty()) {
+        const int D = b->D, Q = b->vd - 1;
+        const int64_t batch = std::max<int64_t>(1024, (24LL << 20) / D) & ~(int64_t)31;
+        for (int c : b->precise) {
+            for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
+                const int64_t r1 = std::min(n_rows, r0 + batch);
+                const int64_t rows_pad = (r1 - r0 + 31) & ~(int64_t)31;
+                MixExactParams m{};
+                m.raw = a.d_raw;
+                m.raw_n0 = a.raw_n0;
+                m.raw_len = a.raw_len;
+                m.iq_swap = swap;
+                m.q_neg = neg;
+                m.n0 = (a.mg_begin + r0 - Q) * (int64_t)D;
+                m.count = (rows_pad + Q) * (int64_t)D;
+                m.phase.tab = b->d_phase;
+                m.phase.seg_len = a.seg_len;
+                m.phase.seg0_n = a.seg_origin;
+                m.phase.nseg = a.nseg;
+                m.chan = c;
+                m.w = b->w[c];
+                if ((rc = dev_grow(&b->d_mixed, &b->mixed_cap, (size_t)m.count))) return rc;
+                m.mixed = b->d_mixed;
+                if ((rc = launch_mix_exact(m, b->cfg.codec, a.st))) return rc;
+                if ((rc = launch_fir_decim_f64(b->d_mixed, b->d_taps + b->tap_off[c], (int)b->taps[c].size(), D, Q,
+                                               r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st)))
+                    return rc;
+                b->launches += 2;
+            }
+        }
+    }
     if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[2], a.st));
     // ---- channel-rate tail ------------------------------------------------------------------
     TailParams t{};
@@ -346,6 +385,38 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     t.agc_target = std::pow(10.0, -12.0 / 20.0);  // decoders/ssb.py:21,33
     t.agc_decay = 0.001;                          // decoders/ssb.py:22
     if ((rc = launch_tail(t, b->any_agc, a.st, &b->launches))) return rc;
+    if (!b->precise.empty()) {
+        if ((rc = dev_grow(&b->d_tmp, &b->tmp_cap, (size_t)C * stride))) return rc;
+        SeqParams q{};
+        q.pre = b->d_pre;
+        q.tmp = b->d_tmp;
+        q.work_stride = stride;
+        q.audio = a.d_audio;
+        q.clipped = a.d_clip;
+        q.out_stride = a.out_stride;
+        q.sumsq = t.sumsq;
+        q.nwin = a.nwin;
+        q.win_chunk0 = a.win0;
+        q.state = b->d_state;
+        q.chan_idx = b->d_precise;
+        q.nprecise = (int)b->precise.size();
+        q.chunk0 = 0;
+        q.seg_origin = a.seg_origin;
+        q.seg_len = a.seg_len;
+        q.mg0 = a.mg_begin;
+        q.n = n_rows;
+        q.n_skip = a.mg_emit - a.mg_begin;
+        q.decim = b->D;
+        q.fresh = a.fresh ? 1 : 0;
+        q.agc_target = t.agc_target;
+        q.agc_decay = t.agc_decay;
+        q.repaired = b->d_repaired;
+        const int64_t last_n = (a.mg_end - 1) * (int64_t)b->D;
+        q.nchunks = (int)(std::max<int64_t>(0, last_n - a.seg_origin) / a.seg_len + 1);
+        if ((rc = dev_grow(&b->d_rec, &b->rec_cap, (size_t)q.nprecise * q.nchunks))) return rc;
+        q.rec = b->d_rec;
+        if ((rc = launch_seq_tail(q, a.st, &b->launches))) return rc;
+    }
     if (b->timing) {
         IQ2A_CUDA_TRY(cudaEventRecord(b->ev[3], a.st));
         b->ev_pending = true;
@@ -487,7 +558,19 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         const double tau = std::max(ch[c].deemph_us * 1e-6, 1e-6);
         tc[c].alpha = std::exp(-1.0 / (fs_ch * tau));
         tc[c].beta = 1.0 - tc[c].alpha;
-        if ((ch[c].mode == IQ2A_MODE_USB || ch[c].mode == IQ2A_MODE_LSB) && ch[c].agc_enabled) b->any_agc = true;
+        tc[c].precise = 0;
+        tc[c].pad = 0;
+        if ((ch[c].mode == IQ2A_MODE_USB || ch[c].mode == IQ2A_MODE_LSB) && ch[c].agc_enabled) {
+            const char* env = std::getenv("IQ2A_PRECISE_SSB");
+            const bool off = env && std::strcmp(env, "0") == 0;
+            const size_t fir_smem = (size_t)(32 + vd) * 16 * 8 + (size_t)(vd + 1) * 16 * 8;
+            if (!off && fir_smem <= 200 * 1024) {
+                tc[c].precise = 1;
+                b->precise.push_back(c);
+            } else {
+                b->any_agc = true;       // float64-scan AGC (not bit-faithful)
+            }
+        }
         toff[c] = (int64_t)all_taps.size();
         tn[c] = ch[c].ntaps;
         all_taps.insert(all_taps.end(), b->taps[c].begin(), b->taps[c].end());
@@ -525,6 +608,11 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     ok &= cudaMemcpy(b->d_ntaps, tn.data(), C * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(b->d_w, b->w.data(), C * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMemcpy(b->d_chan, tc.data(), C * sizeof(TailChan), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!b->precise.empty()) {
+        if ((rc = dev_alloc(&b->d_precise, b->precise.size())) || (rc = dev_alloc(&b->d_repaired, (size_t)1))) { cudaFree(d_wtab); return fail(rc); }
+        ok &= cudaMemcpy(b->d_precise, b->precise.data(), b->precise.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemset(b->d_repaired, 0, sizeof(int)) == cudaSuccess;
+    }
     if (!ok) { cudaFree(d_wtab); set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(IQ2A_ERR_CUDA); }
     {
         const char* env = std::getenv("IQ2A_CHANNELIZER");
@@ -543,6 +631,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             if (rc) { cudaFree(d_wtab); return fail(rc); }
             b->launches += b->v2_ok ? 2 : 1;
         }
+    b->tap_off = toff;
     cudaError_t e = cudaStreamSynchronize(b->stream);
     cudaFree(d_wtab);
     if (e != cudaSuccess) { set_error("G-table build failed: %s", cudaGetErrorString(e)); return fail(IQ2A_ERR_CUDA); }
@@ -987,7 +1076,7 @@ int iq2a_demod(int32_t mode, int32_t agc_enabled, double deemph_alpha, const flo
         (rc = agg.alloc(ntiles * sizeof(double2))) || (rc = ss.alloc(sizeof(double))) ||
         (rc = st.alloc(sizeof(iq2a_channel_state))) || (rc = chn.alloc(sizeof(TailChan))))
         return rc;
-    TailChan tc{mode, agc_enabled ? 1 : 0, deemph_alpha, 1.0 - deemph_alpha};
+    TailChan tc{mode, agc_enabled ? 1 : 0, deemph_alpha, 1.0 - deemph_alpha, 0, 0};
     IQ2A_CUDA_TRY(cudaMemcpy(bb.p, in_c64, n * sizeof(float2), cudaMemcpyHostToDevice));
     IQ2A_CUDA_TRY(cudaMemcpy(st.p, state, sizeof(*state), cudaMemcpyHostToDevice));
     IQ2A_CUDA_TRY(cudaMemcpy(chn.p, &tc, sizeof(tc), cudaMemcpyHostToDevice));
@@ -1029,7 +1118,7 @@ int iq2a_scan(int32_t kind, double deemph_alpha, const float* in, int64_t n, iq2
         (rc = agg.alloc(ntiles * sizeof(double2))) || (rc = st.alloc(sizeof(iq2a_channel_state))) ||
         (rc = chn.alloc(sizeof(TailChan))))
         return rc;
-    TailChan tc{MODE_RAW_DEEMPH + kind, 0, deemph_alpha, 1.0 - deemph_alpha};
+    TailChan tc{MODE_RAW_DEEMPH + kind, 0, deemph_alpha, 1.0 - deemph_alpha, 0, 0};
     IQ2A_CUDA_TRY(cudaMemcpy(pre.p, in, n * sizeof(float), cudaMemcpyHostToDevice));
     IQ2A_CUDA_TRY(cudaMemcpy(st.p, state, sizeof(*state), cudaMemcpyHostToDevice));
     IQ2A_CUDA_TRY(cudaMemcpy(chn.p, &tc, sizeof(tc), cudaMemcpyHostToDevice));

@@ -1,0 +1,53 @@
+// Parameters / launchers of the bit-faithful SSB+AGC path (precise.cu).
+#pragma once
+#include "common.cuh"
+#include "../../include/iq2a_b200.h"
+
+namespace iq2a {
+
+struct MixExactParams {
+    const void* raw;
+    int64_t raw_n0, raw_len;
+    int iq_swap, q_neg;
+    int64_t n0;            // global index of mixed[0]
+    int64_t count;
+    PhaseModel phase;      // tab rows indexed by global channel
+    int chan;
+    double w;
+    float2* mixed;
+};
+
+struct SeqChunk {
+    int64_t lo, hi;        // rows of the chunk, relative to row 0 of the call
+    float y_start, y_end;  // DC-blocker state the chunk started from / ended with
+};
+
+struct SeqParams {
+    const float* pre;      // [C][work_stride] real(s)
+    float* tmp;            // [C][work_stride] DC-blocked audio
+    int64_t work_stride;
+    float* audio;          // [C][out_stride] or null
+    float* clipped;
+    int64_t out_stride;
+    double* sumsq;         // [C][nwin] or null
+    int64_t nwin, win_chunk0;
+    iq2a_channel_state* state;
+    const int* chan_idx;   // [nprecise] channel numbers on this path (device)
+    int nprecise;
+    SeqChunk* rec;         // [nprecise][nchunks] (device)
+    int nchunks;
+    int64_t chunk0;
+    int64_t seg_origin, seg_len;
+    int64_t mg0, n, n_skip;
+    int decim;
+    int fresh;
+    double agc_target, agc_decay;
+    int* repaired;         // device counter of serially repaired chunks, or null
+};
+
+int launch_mix_exact(const MixExactParams& p, int codec, cudaStream_t st);
+int launch_fir_decim_f64(const float2* d_mixed, const double* d_taps, int ntaps, int D, int Q, int64_t nrows,
+                         float2* d_out, cudaStream_t st);
+int launch_seq_tail(const SeqParams& p, cudaStream_t st, int64_t* launches);
+
+}  // namespace iq2a

@@ -76,6 +76,7 @@ __global__ void k_pre(const TailParams p) {
 enum ScanKind : int { SCAN_NONE = -1, SCAN_DEEMPH = 0, SCAN_DC = 1, SCAN_AGC = 2 };
 
 __device__ __forceinline__ int scan_kind(const TailChan& ch, int pass) {
+    if (ch.precise) return SCAN_NONE;
     if (pass == 0) {
         if (ch.mode == MODE_NFM || ch.mode == MODE_RAW_DEEMPH) return SCAN_DEEMPH;
         if (ch.mode == MODE_AM || ch.mode == MODE_USB || ch.mode == MODE_LSB || ch.mode == MODE_RAW_DC) return SCAN_DC;
@@ -310,7 +311,8 @@ __global__ void k_state_tail(const TailParams p) {
         p.state[c].prev_re = last.x;
         p.state[c].prev_im = last.y;
     }
-    if (mode == MODE_AM || mode == MODE_USB || mode == MODE_LSB || mode == MODE_RAW_DC)
+    // (channels on the sequential path update their DC-blocker state themselves, after reading it)
+    if (!p.chan[c].precise && (mode == MODE_AM || mode == MODE_USB || mode == MODE_LSB || mode == MODE_RAW_DC))
         p.state[c].dc_x = p.pre[(size_t)c * p.work_stride + p.n - 1];
 }
 

@@ -10,6 +10,8 @@ struct TailChan {
     int agc;         // SSB only
     double alpha;    // de-emphasis pole (decoders/nfm.py:42)
     double beta;     // 1 - alpha
+    int precise;     // 1: the bit-faithful sequential tail (precise.cu) owns this channel
+    int pad;
 };
 
 struct TailParams {
