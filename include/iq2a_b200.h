@@ -198,6 +198,21 @@ int iq2a_demod(int32_t mode, int32_t agc_enabled, double deemph_alpha, const flo
 int iq2a_scan(int32_t kind, double deemph_alpha, const float* in, int64_t n, iq2a_channel_state* state,
               float* out, int32_t device);
 
+/* ---- 48 kHz output stage: what the encode-side ffmpeg subprocess computes (processing.py:399-418:
+ *      `-f f32le -ar round(fs_ch) -i - -acodec pcm_s16le -ar 48000`), i.e. libswresample's default
+ *      resampler + flt->s16, for C channels at once.  Streaming: process() returns every output
+ *      whose filter window is complete, flush() the tail (reflection, like swr_convert(NULL)). ---- */
+typedef struct iq2a_resampler iq2a_resampler;
+int  iq2a_resampler_create(int32_t in_rate, int32_t out_rate, int32_t n_channels, int32_t device,
+                           iq2a_resampler** out);
+void iq2a_resampler_destroy(iq2a_resampler* r);
+/* audio: host float32 [C][in_stride], n samples per channel; pcm: host int16 [C][out_stride] */
+int  iq2a_resampler_process(iq2a_resampler* r, const float* audio, int64_t n, int64_t in_stride,
+                            int16_t* pcm, int64_t out_stride, int64_t* n_out);
+int  iq2a_resampler_flush(iq2a_resampler* r, int16_t* pcm, int64_t out_stride, int64_t* n_out);
+/* upper bound of the outputs a process()/flush() call can return after n_in more input samples */
+int  iq2a_resampler_max_outputs(const iq2a_resampler* r, int64_t n_in, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,8 @@ SYMBOLS = (
     "iq2a_bank_process_resident", "iq2a_bank_process_resident_async", "iq2a_bank_launch_count",
     "iq2a_bank_copy_gtable", "iq2a_bank_set_timing", "iq2a_bank_get_timing",
     "iq2a_unpack_mix", "iq2a_fir", "iq2a_decimate", "iq2a_demod", "iq2a_scan",
+    "iq2a_resampler_create", "iq2a_resampler_destroy", "iq2a_resampler_process", "iq2a_resampler_flush",
+    "iq2a_resampler_max_outputs",
 )
 
 
@@ -102,9 +104,15 @@ def load() -> C.CDLL:
     lib.iq2a_decimate.argtypes = [fp, i64, i32, i64, fp, C.POINTER(i64), i32]
     lib.iq2a_demod.argtypes = [i32, i32, f64, fp, i64, C.POINTER(ChannelState), fp, C.POINTER(f64), i32]
     lib.iq2a_scan.argtypes = [i32, f64, fp, i64, C.POINTER(ChannelState), fp, i32]
+    lib.iq2a_resampler_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    lib.iq2a_resampler_destroy.argtypes = [vp]
+    lib.iq2a_resampler_destroy.restype = None
+    lib.iq2a_resampler_process.argtypes = [vp, fp, i64, i64, fp, i64, C.POINTER(i64)]
+    lib.iq2a_resampler_flush.argtypes = [vp, fp, i64, C.POINTER(i64)]
+    lib.iq2a_resampler_max_outputs.argtypes = [vp, i64, C.POINTER(i64)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("iq2a_last_error", "iq2a_bank_destroy"):
+        if name not in ("iq2a_last_error", "iq2a_bank_destroy", "iq2a_resampler_destroy"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -266,7 +266,8 @@ class AudioWriter:
         self._error: BaseException | None = None
         self.proc = None
         self._wav = None
-        ffmpeg = resolve_ffmpeg_executable()
+        self._res = None
+        ffmpeg = None if os.environ.get("IQ_TO_AUDIO_B200_NATIVE_WAV") == "1" else resolve_ffmpeg_executable()
         if ffmpeg is None and require_ffmpeg:
             raise RuntimeError(FFMPEG_HINT)
         self.output_path.parent.mkdir(parents=True, exist_ok=True)
@@ -281,11 +282,15 @@ class AudioWriter:
             self._thread = threading.Thread(target=self._drain, name="AudioWriter", daemon=True)
             self._thread.start()
         else:
-            LOG.warning("ffmpeg not found: writing %d Hz PCM_16 without the 48 kHz resample.", self.ffmpeg_rate)
+            from .resample import Resampler48k
+            LOG.info("Encoding natively: %d Hz float32 -> 48 kHz PCM_16 on the GPU.", self.ffmpeg_rate)
+            self._res = Resampler48k(self.ffmpeg_rate, 1) if self.ffmpeg_rate > 48_000 else None
+            if self._res is None and self.ffmpeg_rate != 48_000:
+                raise RuntimeError(f"channel rate {self.ffmpeg_rate} Hz is below 48 kHz: ffmpeg is required to upsample")
             self._wav = wave.open(str(self.output_path), "wb")
             self._wav.setnchannels(1)
             self._wav.setsampwidth(2)
-            self._wav.setframerate(self.ffmpeg_rate)
+            self._wav.setframerate(48_000)
 
     def _drain(self) -> None:
         pipe = self.proc.stdin
@@ -314,8 +319,10 @@ class AudioWriter:
             return
         if self.proc is not None:
             self._queue.put(np.ascontiguousarray(safe, dtype=np.float32).tobytes())
-        else:
-            pcm = np.clip(np.rint(safe.astype(np.float64) * 32768.0), -32768, 32767).astype("<i2")
+        elif self._res is not None:
+            self._wav.writeframes(self._res.process(safe)[0].astype("<i2").tobytes())
+        else:   # already 48 kHz: swr's flt -> s16 conversion only
+            pcm = np.clip(np.rint(safe.astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype("<i2")
             self._wav.writeframes(pcm.tobytes())
 
     def close(self) -> None:
@@ -336,6 +343,9 @@ class AudioWriter:
             if self._error:
                 raise RuntimeError("ffmpeg writer failed") from self._error
         elif self._wav is not None:
+            if self._res is not None:
+                self._wav.writeframes(self._res.flush()[0].astype("<i2").tobytes())
+                self._res.close()
             self._wav.close()
 
 

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import iq_oracle as orc
+from oracle.swr_model import SwrModel
 from tests import _cases
 
 pytestmark = pytest.mark.gpu
@@ -26,8 +27,8 @@ def _read_pcm(path):
 
 @pytest.fixture()
 def no_ffmpeg(monkeypatch):
-    # force the native writer (PCM_16 at the channel rate) so the samples can be compared one to one
-    monkeypatch.setenv("IQ_TO_AUDIO_FFMPEG", "/nonexistent/ffmpeg")
+    # force the native encoder (GPU resampler to 48 kHz + PCM_16) even where an ffmpeg binary exists
+    monkeypatch.setenv("IQ_TO_AUDIO_B200_NATIVE_WAV", "1")
 
 
 def test_pipeline_five_targets_one_pass(tmp_path, no_ffmpeg):
@@ -45,9 +46,9 @@ def test_pipeline_five_targets_one_pass(tmp_path, no_ffmpeg):
         g = _cases.load(f"case_b_nfm_10M_t{i}")
         assert r.decimation == 104 and r.mix_sign == 1 and r.output_path.name == f"out_{int(round(r.target_freq))}.wav"
         rate, pcm = _read_pcm(r.output_path)
-        assert rate == 96_154 and pcm.size == g["audio"].size                     # ref processing.py:391
-        want = np.clip(np.rint(g["clipped"].astype(np.float64) * 32768.0), -32768, 32767)
-        assert np.abs(pcm.astype(np.int64) - want).max() <= 1                     # +-1 LSB
+        want = SwrModel(96_154).resample_s16(g["clipped"])        # ffmpeg is told round(fs_ch) = 96154 (ref :391)
+        assert rate == 48_000 and pcm.size == want.size
+        assert np.abs(pcm.astype(np.int64) - want.astype(np.int64)).max() <= 1    # +-1 LSB on the int16 WAV
         assert abs(r.audio_peak - float(g["peak"])) <= 1e-5
 
 
@@ -61,11 +62,12 @@ def test_pipeline_auto_mix_sign_and_preview(tmp_path, no_ffmpeg):
     assert r.mix_sign == int(g["mix_sign"]) and r.decimation == 26
     assert r.samples_processed == 150_000
     rate, pcm = _read_pcm(tmp_path / "a.wav")
-    assert pcm.size == orc.decimated_count(0, 150_000, 26)
+    rows = orc.decimated_count(0, 150_000, 26)
     # the reference tunes the chunk to 1 Mi at 2.5 MS/s: the 150 000-sample preview is one chunk, NFM has no
-    # per-chunk semantics, so the first samples equal the golden stream's
-    want = np.clip(np.rint(g["clipped"][:pcm.size].astype(np.float64) * 32768.0), -32768, 32767)
-    assert np.abs(pcm.astype(np.int64) - want).max() <= 1
+    # per-chunk semantics, so the channel-rate audio equals the head of the golden stream
+    want = SwrModel(96_154).resample_s16(g["clipped"][:rows])
+    assert rate == 48_000 and pcm.size == want.size
+    assert np.abs(pcm.astype(np.int64) - want.astype(np.int64)).max() <= 1
 
 
 def test_pipeline_cancel_removes_output(tmp_path, no_ffmpeg):
@@ -113,3 +115,33 @@ def test_pipeline_errors(tmp_path, no_ffmpeg):
                                             input_sample_rate=2.5e6, output_path=tmp_path / "r.wav",
                                             mix_sign_override=1)).run()
     assert r.samples_processed == 10_000
+
+
+@pytest.mark.parametrize("key,pieces", [("r96154_n100991", [40_330, 40_330, 20_331]), ("r96000_n26219", [6_554, 6_554, 6_554, 6_557]),
+                                        ("r95238_n20000", [20_000]), ("r100000_n12345", [5_000, 7_345]), ("r96154_n333", [333])])
+def test_gpu_resampler_matches_libswresample_vectors(key, pieces):
+    """K14 on the GPU against vectors from the real libswresample: sample counts exact (per call and
+    after flush), int16 within +-1 LSB."""
+    from iq_to_audio_b200.resample import Resampler48k
+    rv = _cases.load("resampler_vectors")
+    in_rate = int(key.split("_")[0][1:])
+    x = rv[key + "_in"]
+    model = SwrModel(in_rate)
+    res = Resampler48k(in_rate, 2)                         # two channels: x and -x
+    outs, pos = [], 0
+    for n in pieces:
+        outs.append(res.process(np.stack([x[pos:pos + n], -x[pos:pos + n]])))
+        pos += n
+    outs.append(res.flush())
+    res.close()
+    got = np.concatenate(outs, axis=1)
+    ref = rv[key + "_s16"]
+    assert got.shape == (2, ref.size)
+    if key + "_counts" in rv and len(pieces) == len(rv[key + "_counts"]) - 1:
+        assert [o.shape[1] for o in outs] == list(rv[key + "_counts"])          # per-call counts as the library's
+    assert np.abs(got[0].astype(np.int64) - ref.astype(np.int64)).max() <= 1
+    assert np.mean(got[0] == ref) > 0.995
+    assert np.abs(got[0].astype(np.int64) - model.resample_s16(x).astype(np.int64)).max() <= 1
+    assert np.abs(got[1].astype(np.int64) + got[0].astype(np.int64)).max() <= 1   # odd symmetry up to rounding ties
+    with pytest.raises(ValueError):
+        Resampler48k(48_000, 1)
