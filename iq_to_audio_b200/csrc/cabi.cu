@@ -123,6 +123,7 @@ struct iq2a_bank {
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     bool v2_ok = false;
+    int kernel_gen = 1;             // 3: warp-specialised kernel, 2: TMA + packed transforms, 1: first generation
     float2* d_tw = nullptr;
     double* d_taps = nullptr;
     int64_t* d_tap_off = nullptr;
@@ -283,7 +284,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
             p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
             p.gtab = b->d_gtab2 + g.g_off;
             p.out = b->d_bb + (size_t)g.first * stride;
-            if ((rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st))) return rc;
+            if ((rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st, b->kernel_gen))) return rc;
             b->launches++;
             b->launches_v2++;
         }
@@ -618,6 +619,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         const char* env = std::getenv("IQ2A_CHANNELIZER");
         const bool force_v1 = env && std::strcmp(env, "v1") == 0;
         b->v2_ok = !force_v1 && M == 512 && cfg->codec == IQ2A_CODEC_S16 && D % 4 == 0 && channelize2_available();
+        b->kernel_gen = !b->v2_ok ? 1 : (env && std::strcmp(env, "v2") == 0) ? 2 : (env && std::strcmp(env, "v3") == 0) ? 3 : 4;
         if (b->v2_ok && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
     }
     for (const Group& g : b->groups)
@@ -651,7 +653,7 @@ int iq2a_bank_info_get(const iq2a_bank* b, iq2a_bank_info* info) {
     info->hop = (int64_t)b->ld * b->D;
     info->halo = (int64_t)b->vd * b->D;
     info->fs_channel = b->cfg.sample_rate / b->D;
-    info->kernel_generation = b->v2_ok ? 2 : 1;
+    info->kernel_generation = b->kernel_gen;
     info->reserved = 0;
     return IQ2A_OK;
 }

@@ -26,6 +26,10 @@ int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, i
 
 #define IQ2A_DECL2(CG) int launch_channelize2_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
 IQ2A_DECL2(1) IQ2A_DECL2(2) IQ2A_DECL2(3) IQ2A_DECL2(4) IQ2A_DECL2(5) IQ2A_DECL2(6)
+#define IQ2A_DECL2B(CG) int launch_channelize2b_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
+IQ2A_DECL2B(1) IQ2A_DECL2B(2) IQ2A_DECL2B(3) IQ2A_DECL2B(4) IQ2A_DECL2B(5) IQ2A_DECL2B(6)
+#define IQ2A_DECL3(CG) int launch_channelize3_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
+IQ2A_DECL3(1) IQ2A_DECL3(2) IQ2A_DECL3(3) IQ2A_DECL3(4) IQ2A_DECL3(5) IQ2A_DECL3(6)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -50,19 +54,36 @@ bool channelize2_available() { return encode_tiled_fn() != nullptr; }
 // Second-generation kernel over rows [p.mg_begin, p.mg_end): `base` points at the int16 frame whose global
 // index is tmap_row0 * D (16-byte aligned), `rows` complete rows of D frames are readable from there.
 int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
-                       int n_sm, cudaStream_t st) {
+                       int n_sm, cudaStream_t st, int generation) {
     if (p.nblocks <= 0) return IQ2A_OK;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return IQ2A_ERR_STATE; }
     CUtensorMap tmap;
     const cuuint64_t dims[2] = {(cuuint64_t)p.decim, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)p.decim * 4};
-    const cuuint32_t box[2] = {8, 172};
+    // generation 2: tiles of 8 branches x 3 boxes of 172 rows; generation 3: 4 branches x 4 boxes of 136 rows
+    const cuuint32_t box[2] = {generation == 3 ? 4u : 8u, generation == 3 ? 136u : 172u};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return IQ2A_ERR_CUDA; }
+    if (generation == 4) {      // generation 2 with two blocks per set and two CTAs per SM
+        switch (cg) {
+#define IQ2A_CASE2B(CG) case CG: return launch_channelize2b_##CG(p, tmap, tmap_row0, n_sm, st);
+            IQ2A_CASE2B(1) IQ2A_CASE2B(2) IQ2A_CASE2B(3) IQ2A_CASE2B(4) IQ2A_CASE2B(5) IQ2A_CASE2B(6)
+        }
+        set_error("unsupported channel group %d", cg);
+        return IQ2A_ERR_INVALID;
+    }
+    if (generation == 3) {
+        switch (cg) {
+#define IQ2A_CASE3(CG) case CG: return launch_channelize3_##CG(p, tmap, tmap_row0, n_sm, st);
+            IQ2A_CASE3(1) IQ2A_CASE3(2) IQ2A_CASE3(3) IQ2A_CASE3(4) IQ2A_CASE3(5) IQ2A_CASE3(6)
+        }
+        set_error("unsupported channel group %d", cg);
+        return IQ2A_ERR_INVALID;
+    }
     switch (cg) {
 #define IQ2A_CASE2(CG) case CG: return launch_channelize2_##CG(p, tmap, tmap_row0, n_sm, st);
         IQ2A_CASE2(1) IQ2A_CASE2(2) IQ2A_CASE2(3) IQ2A_CASE2(4) IQ2A_CASE2(5) IQ2A_CASE2(6)

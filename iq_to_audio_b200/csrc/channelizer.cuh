@@ -46,18 +46,17 @@ struct Geo<1024> {
 // Inverse M-point transforms of the output spectra held in `tile` ([slot j'][YS] float2, j' = k1*R2 + k2
 // <-> bin k1 + R1*k2), overlap rows dropped, NCO rotation at the channel rate, complex64 store.
 // Shared by both channel-bank kernels.  Ends with the tile free for reuse (caller syncs).
-template <int M, int CG>
+template <int M, int CG, int BT = kBlocksPerSet, int NT = kThreads>
 __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw, const ChannelizeParams& p, int blk0) {
     using G = Geo<M>;
     constexpr int R1 = G::R1, R2 = G::R2;
-    constexpr int BT = kBlocksPerSet;
     constexpr int NS = CG * BT;
     constexpr int YS = NS | 1;
     const int tid = threadIdx.x;
     const int D = p.decim;
     __syncthreads();
     // inverse pass A: for each k1, R2-point inverse over k2, then W_M^{-m2*k1}
-    for (int idx = tid; idx < R1 * NS; idx += kThreads) {
+    for (int idx = tid; idx < R1 * NS; idx += NT) {
         const int sy = idx % NS, k1 = idx / NS;
         float2 v[R2];
         float2* base = tile + (k1 * R2) * YS + sy;
@@ -73,7 +72,7 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
     }
     __syncthreads();
     // inverse pass B: for each m2, R1-point inverse over k1 -> y[R2*m1 + m2]
-    for (int idx = tid; idx < R2 * NS; idx += kThreads) {
+    for (int idx = tid; idx < R2 * NS; idx += NT) {
         const int sy = idx % NS, m2 = idx / NS;
         float2 v[R1];
         float2* base = tile + m2 * YS + sy;
@@ -88,14 +87,24 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
     __syncthreads();
     // ---------------- drop the overlap rows, rotate by the NCO, store ------------------------
     const int ld = p.ld;
-    for (int idx = tid; idx < NS * ld; idx += kThreads) {
+    // reference chunk of the first row of this block set: one 64-bit division per thread, then the
+    // chunk index of every output follows by comparison (a block set spans at most a few chunks)
+    const int64_t n_first = (p.mg_begin + (int64_t)blk0 * ld) * (int64_t)D - p.phase.seg0_n;
+    int64_t k_first = n_first >= 0 ? n_first / p.phase.seg_len : 0;
+    if (k_first >= p.phase.nseg) k_first = p.phase.nseg - 1;
+    for (int idx = tid; idx < NS * ld; idx += NT) {
         const int r = idx % ld, sy = idx / ld;
         const int b = sy / CG, c = sy % CG;
         const int blk = blk0 + b;
         const int64_t mg = p.mg_begin + (int64_t)blk * ld + r;
         if (blk < p.nblocks && mg < p.mg_end && c < p.nchan) {
             const float2 y = tile[(p.vd + r) * YS + sy];
-            const float2 lo = phasor_f32(nco_phase(p.phase, c, p.w[c], mg * (int64_t)D));
+            const int64_t rel = mg * (int64_t)D - p.phase.seg0_n;
+            int64_t k = k_first;
+            while (k + 1 < p.phase.nseg && rel >= (k + 1) * p.phase.seg_len) ++k;
+            const int64_t local = rel - k * p.phase.seg_len;
+            const double ph = __dadd_rn(p.phase.tab[(int64_t)c * p.phase.nseg + k], __dmul_rn(p.w[c], (double)local));
+            const float2 lo = phasor_f32(ph);
             p.out[(size_t)c * p.out_stride + (mg - p.mg_begin)] = cmul(y, lo);
         }
     }

@@ -28,6 +28,18 @@ constexpr int kStageRows = 516;                    // 512 + rotation slack, 3 TM
 constexpr int kBoxRows = 172;
 constexpr int kStageBytes = kStageRows * 32;       // per block: rows of 8 frames x 4 B
 constexpr int kTileBytes2 = 256 * 33 * 16;
+// BT blocks per set: 4 -> 512 threads, one CTA per SM; 2 -> 256 threads and ~111 KB of shared memory, so
+// TWO CTAs share an SM and the hardware overlaps one CTA's FFMA-bound MAC phase with the other's
+// ALU/LSU-bound transform passes (each G element is then reused for 2 blocks instead of 4).
+template <int BT>
+struct Geo2 {
+    static constexpr int NT = 128 * BT;            // threads
+    static constexpr int LW = 8 * BT;              // lane slots per tile (BT blocks x 8 branches)
+    static constexpr int RS = LW + 1;              // tile row stride (float4)
+    static constexpr int BPT = 512 / NT;           // spectrum bins per thread in the MAC phase
+    static constexpr size_t tile_bytes = (size_t)256 * RS * 16;
+    static constexpr size_t smem = tile_bytes + (size_t)BT * kStageBytes + 512 * sizeof(float2) + 256 * sizeof(float4) + 16;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,26 +73,27 @@ __host__ __device__ inline int slot_to_bin_v2(int j) {
     return (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
 }
 
-template <int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int BT>
+__global__ void __launch_bounds__(Geo2<BT>::NT, 4 / BT)
 k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap, const int64_t tmap_row0) {
-    constexpr int BT = kBlocksPerSet, P = 8, RS = 33;
+    using G2 = Geo2<BT>;
+    constexpr int P = 8, RS = G2::RS, NT = G2::NT, LW = G2::LW, BPT = G2::BPT;
     constexpr int NS = CG * BT, YS = NS | 1;
-    static_assert(BT == 4 && (size_t)512 * YS * sizeof(float2) <= (size_t)kTileBytes2, "layout");
+    static_assert((BT == 4 || BT == 2) && (size_t)512 * YS * sizeof(float2) <= G2::tile_bytes, "layout");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* T = reinterpret_cast<float4*>(smem_raw);
-    unsigned char* stage = smem_raw + kTileBytes2;
+    unsigned char* stage = smem_raw + G2::tile_bytes;
     float2* tw512 = reinterpret_cast<float2*>(stage + BT * kStageBytes);
     float4* tw256b = reinterpret_cast<float4*>(tw512 + 512);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw256b + 256);
 
     const int tid = threadIdx.x;
-    const int slot = tid & 31, rg = tid >> 5;
+    const int slot = tid % LW, rg = tid / LW;          // 16 row groups either way
     const int b_slot = slot >> 3, pl = slot & 7;
 
-    for (int i = tid; i < 512; i += kThreads) tw512[i] = p.twid[i];
-    for (int i = tid; i < 256; i += kThreads) {
+    for (int i = tid; i < 512; i += NT) tw512[i] = p.twid[i];
+    for (int i = tid; i < 256; i += NT) {
         const float2 w = p.twid[2 * i];                       // W_256^i = W_512^{2i} = (cos, -sin)
         tw256b[i] = make_float4(w.x, w.x, w.y, w.y);
     }
@@ -92,25 +105,23 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
     const int nsets = (p.nblocks + BT - 1) / BT;
     uint32_t parity = 0;
 
-    // MAC-phase identity of this thread: row r of T, upper/lower half of the spectrum
-    const int r_mac = tid & 255, hb = tid >> 8;
-    float2 wc;
-    {
-        const int kq = (r_mac >> 4) + 16 * (r_mac & 15);      // bin within the 256-point halves
-        const float2 w = p.twid[kq];                          // W_512^{k'}
-        wc = hb ? make_float2(-w.x, -w.y) : w;
-    }
-    const int kbin = slot_to_bin_v2(tid);
-    const int yrow = (kbin & 31) * 16 + (kbin >> 5);          // slot the inverse transform expects
-    const float2* __restrict__ gp = p.gtab + tid;
+    // MAC-phase identity of this thread: row r of T; with 512 threads one half of the spectrum each
+    // (bin k' or k'+256), with 256 threads both halves
+    const int r_mac = tid & 255, hb0 = tid >> 8;
+    const int kq = (r_mac >> 4) + 16 * (r_mac & 15);          // bin within the 256-point halves
+    const float2 wq = p.twid[kq];                             // W_512^{k'}
+    const float2 wc = (BPT == 1 && hb0) ? make_float2(-wq.x, -wq.y) : wq;
+    const float2* __restrict__ gp = p.gtab + (BPT == 1 ? tid : r_mac);
 
     for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
         const int blk0 = set * BT;
-        float2 acc[CG][BT];
+        float2 acc[BPT][CG][BT];
 #pragma unroll
-        for (int c = 0; c < CG; ++c)
+        for (int h = 0; h < BPT; ++h)
 #pragma unroll
-            for (int b = 0; b < BT; ++b) acc[c][b] = make_float2(0.f, 0.f);
+            for (int c = 0; c < CG; ++c)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[h][c][b] = make_float2(0.f, 0.f);
 
         auto issue = [&](int t) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -152,7 +163,7 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                     im[m1] = p.q_neg ? pk_sub(pk_bc(8421376.0f), uq) : pk_add(uq, pk_bc(-8421376.0f));
                 }
                 pk_dif<16>(re, im);
-                ulonglong2* dst = reinterpret_cast<ulonglong2*>(T) + m2 * RS + slot;
+                pk_t* dst = reinterpret_cast<pk_t*>(T) + 2 * (m2 * RS + slot);
                 static_for<16>([&](auto kc) {
                     constexpr int k1 = decltype(kc)::value;
                     pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
@@ -164,7 +175,8 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                         xr = nr;
                         xi = ni;
                     }
-                    dst[(k1 * 16) * RS] = make_ulonglong2(xr, xi);
+                    dst[2 * (k1 * 16) * RS] = xr;
+                    dst[2 * (k1 * 16) * RS + 1] = xi;
                 });
             }
             __syncthreads();
@@ -181,48 +193,55 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                     im[i] = v.y;
                 }
                 pk_dif<16>(re, im);
+                pk_t* base64 = reinterpret_cast<pk_t*>(base);
                 static_for<16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
-                    base[k2 * RS] = make_ulonglong2(re[bitrev<16>(k2)], im[bitrev<16>(k2)]);
+                    base64[2 * k2 * RS] = re[bitrev<16>(k2)];
+                    base64[2 * k2 * RS + 1] = im[bitrev<16>(k2)];
                 });
             }
             // G for the first two steps of this tile is requested before the barrier so that the L2 round
             // trip overlaps the wait; inside the loop the table is fetched two steps ahead.
-            float2 g0[CG], g1[CG];
-            {
-                const int pa = t * P, pb1 = min(t * P + 1, D - 1);
+            auto gload = [&](float2 (&g)[BPT][CG], int pb) {
+                const int pn = min(pb, D - 1);
 #pragma unroll
-                for (int c = 0; c < CG; ++c) {
-                    g0[c] = __ldg(gp + ((size_t)pa * CG + c) * 512);
-                    g1[c] = __ldg(gp + ((size_t)pb1 * CG + c) * 512);
-                }
-            }
+                for (int c = 0; c < CG; ++c)
+#pragma unroll
+                    for (int h = 0; h < BPT; ++h) g[h][c] = __ldg(gp + ((size_t)pn * CG + c) * 512 + 256 * h);
+            };
+            float2 g0[BPT][CG], g1[BPT][CG];
+            gload(g0, t * P);
+            gload(g1, t * P + 1);
             __syncthreads();
             // ------------- last radix-2 stage fused with the multiply-accumulate --------------------------
             const float4* trow = T + r_mac * RS;
-            auto mac_step = [&](int q, const float2 (&g)[CG]) {
+            auto mac_step = [&](int q, const float2 (&g)[BPT][CG]) {
 #pragma unroll
                 for (int b = 0; b < BT; ++b) {
                     const float4 v = trow[b * P + q];                    // (E.re, O.re, E.im, O.im)
-                    const float xr = fmaf(wc.x, v.y, fmaf(-wc.y, v.w, v.x));
-                    const float xi = fmaf(wc.x, v.w, fmaf(wc.y, v.y, v.z));
-#pragma unroll
-                    for (int c = 0; c < CG; ++c) {
-                        acc[c][b].x = fmaf(g[c].x, xr, acc[c][b].x);
-                        acc[c][b].x = fmaf(-g[c].y, xi, acc[c][b].x);
-                        acc[c][b].y = fmaf(g[c].x, xi, acc[c][b].y);
-                        acc[c][b].y = fmaf(g[c].y, xr, acc[c][b].y);
+                    float xr[BPT], xi[BPT];
+                    if constexpr (BPT == 1) {
+                        xr[0] = fmaf(wc.x, v.y, fmaf(-wc.y, v.w, v.x));
+                        xi[0] = fmaf(wc.x, v.w, fmaf(wc.y, v.y, v.z));
+                    } else {
+                        const float pr = fmaf(wc.x, v.y, -wc.y * v.w), pi = fmaf(wc.x, v.w, wc.y * v.y);
+                        xr[0] = v.x + pr; xi[0] = v.z + pi;
+                        xr[BPT - 1] = v.x - pr; xi[BPT - 1] = v.z - pi;
                     }
-                }
-            };
-            auto gload = [&](float2 (&g)[CG], int pb) {
-                const int pn = min(pb, D - 1);
 #pragma unroll
-                for (int c = 0; c < CG; ++c) g[c] = __ldg(gp + ((size_t)pn * CG + c) * 512);
+                    for (int h = 0; h < BPT; ++h)
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) {
+                            acc[h][c][b].x = fmaf(g[h][c].x, xr[h], acc[h][c][b].x);
+                            acc[h][c][b].x = fmaf(-g[h][c].y, xi[h], acc[h][c][b].x);
+                            acc[h][c][b].y = fmaf(g[h][c].x, xi[h], acc[h][c][b].y);
+                            acc[h][c][b].y = fmaf(g[h][c].y, xr[h], acc[h][c][b].y);
+                        }
+                }
             };
             if (t * P + P <= D) {
                 // full tile: statically rotated register sets, no copies
-                float2 g2[CG];
+                float2 g2[BPT][CG];
                 static_for<P>([&](auto qc) {
                     constexpr int q = decltype(qc)::value;
                     if constexpr (q % 3 == 0) { gload(g2, t * P + q + 2); mac_step(q, g0); }
@@ -231,14 +250,16 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                 });
             } else {
                 for (int q = 0; q < P && t * P + q < D; ++q) {
-                    float2 g2[CG];
+                    float2 g2[BPT][CG];
                     gload(g2, t * P + q + 2);
                     mac_step(q, g0);
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) {
-                        g0[c] = g1[c];
-                        g1[c] = g2[c];
-                    }
+                    for (int h = 0; h < BPT; ++h)
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) {
+                            g0[h][c] = g1[h][c];
+                            g1[h][c] = g2[h][c];
+                        }
                 }
             }
             __syncthreads();
@@ -247,28 +268,32 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
         // ------------- output spectra -> shared (layout of the shared inverse), inverse, store -------------
         float2* ytile = reinterpret_cast<float2*>(T);
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
+        for (int h = 0; h < BPT; ++h) {
+            const int kbin = kq + 256 * (BPT == 1 ? hb0 : h);
+            const int yrow = (kbin & 31) * 16 + (kbin >> 5);      // slot the inverse transform expects
 #pragma unroll
-            for (int c = 0; c < CG; ++c) ytile[yrow * YS + b * CG + c] = acc[c][b];
-        inverse_and_store<512, CG>(ytile, tw512, p, blk0);
+            for (int b = 0; b < BT; ++b)
+#pragma unroll
+                for (int c = 0; c < CG; ++c) ytile[yrow * YS + b * CG + c] = acc[h][c][b];
+        }
+        inverse_and_store<512, CG, BT, NT>(ytile, tw512, p, blk0);
         __syncthreads();
     }
 }
 
-constexpr size_t kSmem2 = (size_t)kTileBytes2 + kBlocksPerSet * kStageBytes + 512 * sizeof(float2) + 256 * sizeof(float4) + 16;
-
-template <int CG>
+template <int CG, int BT>
 static int launch_channelize2_cg(const ChannelizeParams& p, const CUtensorMap& tmap, int64_t tmap_row0, int n_sm,
                                  cudaStream_t st) {
-    auto kern = k_channelize2<CG>;
+    auto kern = k_channelize2<CG, BT>;
     static bool configured = false;
     if (!configured) {
-        IQ2A_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+        IQ2A_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo2<BT>::smem));
         configured = true;
     }
-    const int nsets = (p.nblocks + kBlocksPerSet - 1) / kBlocksPerSet;
-    const int grid = nsets < n_sm ? nsets : n_sm;
-    kern<<<grid, kThreads, kSmem2, st>>>(p, tmap, tmap_row0);
+    const int nsets = (p.nblocks + BT - 1) / BT;
+    const int slots = n_sm * (4 / BT);                      // persistent: one (BT=4) or two (BT=2) CTAs per SM
+    const int grid = nsets < slots ? nsets : slots;
+    kern<<<grid, Geo2<BT>::NT, Geo2<BT>::smem, st>>>(p, tmap, tmap_row0);
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }

@@ -35,6 +35,6 @@ int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, i
 int channelize_max_group(int m_fft);
 bool channelize2_available();
 int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
-                       int n_sm, cudaStream_t st);
+                       int n_sm, cudaStream_t st, int generation);
 
 }  // namespace iq2a

@@ -262,8 +262,9 @@ def test_stream_case_e_preview_truncation(gpu):
 
 @pytest.mark.parametrize("order", ["iq", "qi_inv"])
 def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
-    """The TMA / packed-f32x2 kernel (generation 2) and the bounds-checked kernel (generation 1)
-    implement the same arithmetic: same capture, ragged call sizes -> same channel samples."""
+    """The warp-specialised kernel (generation 3), the TMA / packed-f32x2 kernel (generation 2) and the
+    bounds-checked kernel (generation 1) implement the same arithmetic: same capture, ragged call sizes
+    -> same channel samples."""
     fs, d = 10e6, 104
     taps = orc.channel_taps(fs, 12_500.0, d)
     rng = np.random.default_rng(17)
@@ -282,12 +283,18 @@ def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
                     parts.append(bank.process_chunk(raw[2 * pos:2 * e], want_baseband=True).baseband.copy())
                 pos = e
             return gen, np.concatenate(parts, axis=1)
+    gen4, bb4 = run()
+    monkeypatch.setenv("IQ2A_CHANNELIZER", "v3")
+    gen3, bb3 = run()
+    monkeypatch.setenv("IQ2A_CHANNELIZER", "v2")
     gen2, bb2 = run()
     monkeypatch.setenv("IQ2A_CHANNELIZER", "v1")
     gen1, bb1 = run()
-    assert (gen2, gen1) == (2, 1)
-    assert bb1.shape == bb2.shape == (3, orc.decimated_count(0, n, d))
+    assert (gen4, gen3, gen2, gen1) == (4, 3, 2, 1)
+    assert bb1.shape == bb2.shape == bb3.shape == bb4.shape == (3, orc.decimated_count(0, n, d))
+    assert np.abs(bb1 - bb4).max() <= 1e-6 * 20_000 / 32768 * 4
     assert np.abs(bb1 - bb2).max() <= 1e-6 * 20_000 / 32768 * 4
+    assert np.abs(bb1 - bb3).max() <= 1e-6 * 20_000 / 32768 * 4
 
 
 def test_pipelined_stream_equals_synchronous_chunks(gpu):
