@@ -347,7 +347,7 @@ def main() -> None:
             traffic = traffic * n_in if traffic is not None else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_channelize2<5>" if bank.kernel_generation == 2 else "k_channelize<512,5,s16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": {4: "k_channelize2<5,2>", 3: "k_channelize3<5>", 2: "k_channelize2<5,4>"}.get(bank.kernel_generation, "k_channelize<512,5,s16>"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_sample": b_alg, "kernel_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1),
                 "peak_source": peak_src}

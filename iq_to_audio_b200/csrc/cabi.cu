@@ -629,7 +629,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
                                 b->d_gtab + g.g_off, g.count, i, 0, 1.0, b->stream);
             if (!rc && b->v2_ok)
                 rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
-                                    b->d_gtab2 + g.g_off, g.count, i, 1, 1.0 / 32768.0, b->stream);
+                                    b->d_gtab2 + g.g_off, g.count, i, b->kernel_gen == 4 ? 2 : 1, 1.0 / 32768.0, b->stream);
             if (rc) { cudaFree(d_wtab); return fail(rc); }
             b->launches += b->v2_ok ? 2 : 1;
         }

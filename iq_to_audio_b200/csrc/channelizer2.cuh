@@ -115,6 +115,8 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
 
     for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
         const int blk0 = set * BT;
+        // BPT == 1: acc[0][c][b] = (re, im) of this thread's bin.  BPT == 2: the two bins k', k'+256 share packed
+        // registers: acc[0][c][b] = (re_k', re_k'+256), acc[1][c][b] = (im_k', im_k'+256) -> FFMA2 multiply-accumulate.
         float2 acc[BPT][CG][BT];
 #pragma unroll
         for (int h = 0; h < BPT; ++h)
@@ -202,12 +204,20 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
             }
             // G for the first two steps of this tile is requested before the barrier so that the L2 round
             // trip overlaps the wait; inside the loop the table is fetched two steps ahead.
+            // BPT == 2 reads table layout 2: per (p, c, r) one float4 (g_k'.x, g_k'+256.x, g_k'.y, g_k'+256.y), i.e.
+            // g[0][c] = packed real parts, g[1][c] = packed imaginary parts of the two bins
             auto gload = [&](float2 (&g)[BPT][CG], int pb) {
                 const int pn = min(pb, D - 1);
 #pragma unroll
-                for (int c = 0; c < CG; ++c)
-#pragma unroll
-                    for (int h = 0; h < BPT; ++h) g[h][c] = __ldg(gp + ((size_t)pn * CG + c) * 512 + 256 * h);
+                for (int c = 0; c < CG; ++c) {
+                    if constexpr (BPT == 1) {
+                        g[0][c] = __ldg(gp + ((size_t)pn * CG + c) * 512);
+                    } else {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(p.gtab) + ((size_t)pn * CG + c) * 256 + r_mac);
+                        g[0][c] = make_float2(v.x, v.y);
+                        g[BPT - 1][c] = make_float2(v.z, v.w);
+                    }
+                }
             };
             float2 g0[BPT][CG], g1[BPT][CG];
             gload(g0, t * P);
@@ -219,24 +229,33 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
                 for (int b = 0; b < BT; ++b) {
                     const float4 v = trow[b * P + q];                    // (E.re, O.re, E.im, O.im)
-                    float xr[BPT], xi[BPT];
                     if constexpr (BPT == 1) {
-                        xr[0] = fmaf(wc.x, v.y, fmaf(-wc.y, v.w, v.x));
-                        xi[0] = fmaf(wc.x, v.w, fmaf(wc.y, v.y, v.z));
-                    } else {
-                        const float pr = fmaf(wc.x, v.y, -wc.y * v.w), pi = fmaf(wc.x, v.w, wc.y * v.y);
-                        xr[0] = v.x + pr; xi[0] = v.z + pi;
-                        xr[BPT - 1] = v.x - pr; xi[BPT - 1] = v.z - pi;
-                    }
-#pragma unroll
-                    for (int h = 0; h < BPT; ++h)
+                        const float xr = fmaf(wc.x, v.y, fmaf(-wc.y, v.w, v.x));
+                        const float xi = fmaf(wc.x, v.w, fmaf(wc.y, v.y, v.z));
 #pragma unroll
                         for (int c = 0; c < CG; ++c) {
-                            acc[h][c][b].x = fmaf(g[h][c].x, xr[h], acc[h][c][b].x);
-                            acc[h][c][b].x = fmaf(-g[h][c].y, xi[h], acc[h][c][b].x);
-                            acc[h][c][b].y = fmaf(g[h][c].x, xi[h], acc[h][c][b].y);
-                            acc[h][c][b].y = fmaf(g[h][c].y, xr[h], acc[h][c][b].y);
+                            acc[0][c][b].x = fmaf(g[0][c].x, xr, acc[0][c][b].x);
+                            acc[0][c][b].x = fmaf(-g[0][c].y, xi, acc[0][c][b].x);
+                            acc[0][c][b].y = fmaf(g[0][c].x, xi, acc[0][c][b].y);
+                            acc[0][c][b].y = fmaf(g[0][c].y, xr, acc[0][c][b].y);
                         }
+                    } else {
+                        // X[k'] = E + W O, X[k'+256] = E - W O, both bins in one packed register pair
+                        const float pr = fmaf(wc.x, v.y, -wc.y * v.w), pi = fmaf(wc.x, v.w, wc.y * v.y);
+                        const pk_t xr = pk_make(v.x + pr, v.x - pr), xi = pk_make(v.z + pi, v.z - pi);
+                        const pk_t nxi = pk_make(-v.z - pi, pi - v.z);
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) {
+                            const pk_t gre = pk_make(g[0][c].x, g[0][c].y), gim = pk_make(g[BPT - 1][c].x, g[BPT - 1][c].y);
+                            pk_t are = pk_make(acc[0][c][b].x, acc[0][c][b].y), aim = pk_make(acc[BPT - 1][c][b].x, acc[BPT - 1][c][b].y);
+                            are = pk_fma(gre, xr, are);
+                            are = pk_fma(gim, nxi, are);
+                            aim = pk_fma(gre, xi, aim);
+                            aim = pk_fma(gim, xr, aim);
+                            pk_split(are, acc[0][c][b].x, acc[0][c][b].y);
+                            pk_split(aim, acc[BPT - 1][c][b].x, acc[BPT - 1][c][b].y);
+                        }
+                    }
                 }
             };
             if (t * P + P <= D) {
@@ -274,7 +293,11 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
             for (int b = 0; b < BT; ++b)
 #pragma unroll
-                for (int c = 0; c < CG; ++c) ytile[yrow * YS + b * CG + c] = acc[h][c][b];
+                for (int c = 0; c < CG; ++c) {
+                    if constexpr (BPT == 1) ytile[yrow * YS + b * CG + c] = acc[0][c][b];
+                    else ytile[yrow * YS + b * CG + c] = h == 0 ? make_float2(acc[0][c][b].x, acc[BPT - 1][c][b].x)
+                                                                : make_float2(acc[0][c][b].y, acc[BPT - 1][c][b].y);
+                }
         }
         inverse_and_store<512, CG, BT, NT>(ytile, tw512, p, blk0);
         __syncthreads();

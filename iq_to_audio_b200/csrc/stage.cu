@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
         if (layout == 0) {
             const int k1 = j / R2, k2 = j % R2;
             bin = k1 + R1 * k2;
-        } else {
+        } else {      // layouts 1 and 2 share the slot -> bin map of the packed-transform kernels
             const int r = j & 255;
             bin = (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
         }
@@ -248,7 +248,14 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
             ar += g.x * t.x - g.y * t.y;
             ai += g.x * t.y + g.y * t.x;
         }
-        gout[((size_t)p * cg + c_in_group) * M + j] = make_float2((float)(ar * inv_m), (float)(ai * inv_m));
+        if (layout == 2) {
+            // two-bins-per-thread kernel: float4 (g_k'.x, g_k'+256.x, g_k'.y, g_k'+256.y) per (p, c, r)
+            float* gf = reinterpret_cast<float*>(gout) + (((size_t)p * cg + c_in_group) * 256 + (j & 255)) * 4;
+            gf[j >> 8] = (float)(ar * inv_m);
+            gf[2 + (j >> 8)] = (float)(ai * inv_m);
+        } else {
+            gout[((size_t)p * cg + c_in_group) * M + j] = make_float2((float)(ar * inv_m), (float)(ai * inv_m));
+        }
     }
 }
 
