@@ -413,3 +413,31 @@ def test_linearity_and_channel_independence_at_scale(gpu):
     assert np.abs(both[0] - alone[0]).max() <= 1e-6
     sa, sb, sab = alone[0], run(b, [T(400e3, taps, 1, "iq")])[0], run((a + b).astype(np.complex64), [T(400e3, taps, 1, "iq")])[0]
     assert np.abs(sa + sb - sab).max() <= 2e-6
+
+
+def test_cfg4_cfg5_shapes_against_oracle(gpu):
+    """61.44 MS/s (D = 640, 32 769 taps): cfg4's five NFM targets and a cfg5-style 16-channel bank
+    (three launch groups) on a short capture, against the CPU oracle run per target."""
+    fs = 61.44e6
+    d, fs_ch = orc.plan_decimation(fs, 96_000.0)
+    assert d == 640
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    assert len(taps) == 32_769
+    n = 1_500_000
+    offs = [(-28.0 + 3.7 * i) * 1e6 for i in range(16)]
+    carriers = [dict(offset=o, amp=0.05, kind="fm", tone=600.0 + 90.0 * i, dev=2500.0) for i, o in enumerate(offs)]
+    raw = orc.to_s16(orc.multi_carrier_capture(fs, n, carriers, noise_std=0.01, seed=5))
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    chunk = 1 << 20
+    T = gpu["Target"]
+    with gpu["ChannelBank"](fs, d, [T(o, taps, 1, "nfm") for o in offs], ref_chunk=chunk) as bank:
+        assert bank.kernel_generation == 4 and bank.fft_size == 512
+        parts = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, n)], want_baseband=True) for s in range(0, n, chunk)]
+        audio = np.concatenate([p.audio for p in parts], axis=1)
+        bb = np.concatenate([p.baseband for p in parts], axis=1)
+    for i in (0, 4, 7, 15):                                   # one channel from each launch group + the last
+        plan = orc.TargetPlan(sample_rate=fs, freq_offset=offs[i], mix_sign=1)
+        want = orc.run_target(x, plan, chunk)
+        assert audio.shape[1] == want.audio.size == orc.decimated_count(0, n, d)
+        assert np.abs(bb[i] - want.baseband).max() <= BB_TOL
+        assert np.abs(audio[i] - want.audio).max() <= AUDIO_TOL
