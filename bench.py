@@ -238,6 +238,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version/info banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n_seg = int(round(FS * args.seconds))
@@ -249,16 +251,32 @@ def main() -> None:
     warm_rows, seg_begin, seg_end, first = seg.warmup_rows, seg.begin, seg.end, seg.first_frame
     capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
-    audio = torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
-    gathered = [torch.empty_like(audio) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # two audio buffers: the NCCL gather of step k (NVLink, rank 0's ingress) runs while step k+1 computes
+    audio_bufs = [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    gathered = [[torch.empty_like(audio_bufs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else None
+    pending = [None, None]
+    step_no = [0]
 
     def resident_step():
+        k = step_no[0] % len(audio_bufs)
+        step_no[0] += 1
+        if pending[k] is not None:          # the gather that last read this buffer must be done
+            pending[k].wait()
+            pending[k] = None
+        audio = audio_bufs[k]
         bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
                               warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
         if world > 1:
-            dist.gather(audio, gathered, dst=0)
+            pending[k] = dist.gather(audio, gathered[k] if gathered else None, dst=0, async_op=True)
+
+    def drain():
+        for k in range(len(pending)):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def sync_all():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -275,6 +293,7 @@ def main() -> None:
         t0 = time.perf_counter()
         for _ in range(steps):
             resident_step()
+        drain()
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
