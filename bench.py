@@ -180,7 +180,24 @@ def cpu_run(n_frames: int, chunk: int, parallel: bool) -> tuple[float, int]:
     return total, 1
 
 
+def _emit(line: dict) -> None:
+    """The one JSON line goes to the REAL stdout; everything else that libraries print to fd 1 during the
+    run (e.g. NCCL's version banner) was diverted to stderr by `_divert_stdout`."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _divert_stdout() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main() -> None:
+    _divert_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -225,7 +242,7 @@ def main() -> None:
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -390,7 +407,7 @@ def main() -> None:
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

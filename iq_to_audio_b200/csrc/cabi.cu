@@ -125,6 +125,7 @@ struct iq2a_bank {
     bool v2_ok = false;
     int kernel_gen = 1;             // 3: warp-specialised kernel, 2: TMA + packed transforms, 1: first generation
     float2* d_tw = nullptr;
+    float2* d_rot = nullptr;        // [C][ld] in-block NCO rotation table
     double* d_taps = nullptr;
     int64_t* d_tap_off = nullptr;
     int* d_ntaps = nullptr;
@@ -157,7 +158,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -272,6 +273,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         p.ld = b->ld;
         p.nchan = g.count;
         p.twid = b->d_tw;
+        p.rot = b->d_rot + (size_t)g.first * b->ld;
         p.out_stride = stride;
         p.phase.tab = b->d_phase + (size_t)g.first * a.nseg;
         p.phase.seg_len = a.seg_len;
@@ -634,6 +636,11 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             b->launches += b->v2_ok ? 2 : 1;
         }
     b->tap_off = toff;
+    if ((rc = dev_alloc(&b->d_rot, (size_t)C * b->ld)) || (rc = launch_build_rot(b->d_w, C, D, b->ld, b->d_rot, b->stream))) {
+        cudaFree(d_wtab);
+        return fail(rc);
+    }
+    b->launches++;
     cudaError_t e = cudaStreamSynchronize(b->stream);
     cudaFree(d_wtab);
     if (e != cudaSuccess) { set_error("G-table build failed: %s", cudaGetErrorString(e)); return fail(IQ2A_ERR_CUDA); }

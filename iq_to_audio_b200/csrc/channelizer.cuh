@@ -87,11 +87,17 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
     __syncthreads();
     // ---------------- drop the overlap rows, rotate by the NCO, store ------------------------
     const int ld = p.ld;
-    // reference chunk of the first row of this block set: one 64-bit division per thread, then the
-    // chunk index of every output follows by comparison (a block set spans at most a few chunks)
-    const int64_t n_first = (p.mg_begin + (int64_t)blk0 * ld) * (int64_t)D - p.phase.seg0_n;
-    int64_t k_first = n_first >= 0 ? n_first / p.phase.seg_len : 0;
-    if (k_first >= p.phase.nseg) k_first = p.phase.nseg - 1;
+    // NCO rotation: phi(mD) is linear in m inside a block, so e^{j phi} = P[b][c] * Q[c][r] with
+    //   P = phasor at the block's first row, evaluated with the reference's exact chunk-wise phase bookkeeping,
+    //   Q[c][r] = e^{j w_c D r}, a per-channel table built once per bank (float64 -> float32).
+    // (A block that straddles a reference chunk boundary inherits the boundary's ~1e-9 rad wrap rounding.)
+    __shared__ float2 s_base[kMaxGroup * kBlocksPerSet];
+    if (tid < NS) {
+        const int b = tid / CG, c = tid % CG;
+        const int64_t mg_b = p.mg_begin + (int64_t)(blk0 + b) * ld;
+        s_base[tid] = phasor_f32(nco_phase(p.phase, c, p.w[c], mg_b * (int64_t)D));
+    }
+    __syncthreads();
     for (int idx = tid; idx < NS * ld; idx += NT) {
         const int r = idx % ld, sy = idx / ld;
         const int b = sy / CG, c = sy % CG;
@@ -99,12 +105,7 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
         const int64_t mg = p.mg_begin + (int64_t)blk * ld + r;
         if (blk < p.nblocks && mg < p.mg_end && c < p.nchan) {
             const float2 y = tile[(p.vd + r) * YS + sy];
-            const int64_t rel = mg * (int64_t)D - p.phase.seg0_n;
-            int64_t k = k_first;
-            while (k + 1 < p.phase.nseg && rel >= (k + 1) * p.phase.seg_len) ++k;
-            const int64_t local = rel - k * p.phase.seg_len;
-            const double ph = __dadd_rn(p.phase.tab[(int64_t)c * p.phase.nseg + k], __dmul_rn(p.w[c], (double)local));
-            const float2 lo = phasor_f32(ph);
+            const float2 lo = cmul(s_base[sy], __ldg(p.rot + (size_t)c * ld + r));
             p.out[(size_t)c * p.out_stride + (mg - p.mg_begin)] = cmul(y, lo);
         }
     }

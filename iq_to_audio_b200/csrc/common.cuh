@@ -38,6 +38,7 @@ struct ChannelizeParams {
     int nchan;           // channels in this launch (<= CG)
     const float2* gtab;  // [D][CG][M], slot order (plan.py: spectrum_slot_to_bin)
     const float2* twid;  // [M] forward twiddles W_M^t
+    const float2* rot;   // [CG][ld] e^{j w_c D r}: in-block part of the NCO rotation
     float2* out;         // [CG][out_stride] complex64 channel samples, index mg - mg_begin
     int64_t out_stride;
     PhaseModel phase;

@@ -259,6 +259,22 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
     }
 }
 
+// in-block NCO rotation table Q[c][r] = exp(j w_c D r), r < ld
+__global__ void k_build_rot(const double* __restrict__ w, int D, int ld, float2* __restrict__ rot) {
+    const int c = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ld) return;
+    double s, co;
+    sincos(w[c] * (double)D * (double)r, &s, &co);
+    rot[(size_t)c * ld + r] = make_float2((float)co, (float)s);
+}
+int launch_build_rot(const double* d_w, int nchan, int D, int ld, float2* d_rot, cudaStream_t st) {
+    const dim3 grid((ld + 127) / 128, nchan);
+    k_build_rot<<<grid, 128, 0, st>>>(d_w, D, ld, d_rot);
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
 int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int R1, int qn,
                    const double2* d_wtab, float2* d_gout, int cg, int c_in_group, int layout, double scale,
                    cudaStream_t st) {

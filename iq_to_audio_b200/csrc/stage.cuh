@@ -31,6 +31,8 @@ int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int 
                    const double2* d_wtab, float2* d_gout, int cg, int c_in_group, int layout, double scale,
                    cudaStream_t st);
 
+int launch_build_rot(const double* d_w, int nchan, int D, int ld, float2* d_rot, cudaStream_t st);
+
 int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, int n_sm, cudaStream_t st);
 int channelize_max_group(int m_fft);
 bool channelize2_available();
