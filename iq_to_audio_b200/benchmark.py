@@ -1,9 +1,11 @@
-"""`--benchmark`: synthetic capture + timed pipeline run (ref: src/iq_to_audio/benchmark.py:41-127).
+"""`--benchmark`: synthetic capture + timed pipeline run.
 
-Same inputs as the reference's harness -- tone at the target offset, AWGN with seed 42, clipped to
-+-0.999, PCM_16 stereo WAV named `benchmark_fc-<fc>Hz.wav` -- and the same log line
-("Benchmark processed N IQ samples in T s (X x realtime)."), plus the throughput in Msamples/s.
-Only `ProcessingPipeline.run()` is timed, as in the reference (benchmark.py:107-109)."""
+Keeps the contract of the reference harness (src/iq_to_audio/benchmark.py:41-127): same keyword
+arguments, same synthetic input (tone at the target offset + AWGN from seed 42, clipped to +-0.999,
+16-bit stereo WAV whose name carries the centre frequency), only `ProcessingPipeline.run()` inside
+the timed region, the "Benchmark processed ... IQ samples in ... s (...x realtime)." report line,
+return code 0.  Adds the throughput in Msamples/s.
+"""
 from __future__ import annotations
 
 import logging
@@ -12,78 +14,95 @@ import tempfile
 import time
 import wave
 from collections.abc import Mapping
+from dataclasses import dataclass
 from pathlib import Path
-from typing import Any
 
 import numpy as np
 
 from .pipeline import ProcessingConfig, ProcessingPipeline
 
 LOG = logging.getLogger(__name__)
+_DEFAULT_CENTER_HZ = 400_000_000.0
+_WAV_BLOCK = 1 << 22
+
+
+@dataclass(frozen=True)
+class _Tuning:
+    center: float
+    target: float
+
+    @property
+    def offset(self) -> float:
+        return self.target - self.center
+
+
+def _resolve_tuning(center: float | None, target: float | None, offset: float) -> _Tuning:
+    """Whichever of centre / target is missing follows from the requested offset."""
+    if center is None and target is None:
+        center = _DEFAULT_CENTER_HZ
+    if center is None:
+        center = target - offset
+    if target is None:
+        target = center + offset
+    return _Tuning(float(center), float(target))
 
 
 def write_synthetic_capture(path: Path, sample_rate: float, seconds: float, freq_offset: float, *,
                             amplitude: float = 0.7, noise_std: float = 0.02) -> int:
+    """Tone + noise capture as PCM_16 stereo WAV; returns the number of complex samples."""
     count = int(round(sample_rate * seconds))
     if count <= 0:
         raise ValueError("Benchmark duration is too short to generate samples.")
-    rng = np.random.default_rng(42)
-    with wave.open(str(path), "wb") as out:
-        out.setnchannels(2)
-        out.setsampwidth(2)
-        out.setframerate(int(sample_rate))
-        noise = rng.normal(scale=noise_std, size=(count, 2))      # one draw, as the reference does
-        step = 1 << 22
-        for s in range(0, count, step):
-            t = np.arange(s, min(s + step, count), dtype=np.float64) / sample_rate
-            lo = np.exp(1j * 2.0 * math.pi * freq_offset * t)
-            iq = np.column_stack((amplitude * lo.real + noise[s:s + t.size, 0],
-                                  amplitude * lo.imag + noise[s:s + t.size, 1])).astype(np.float32)
-            pcm = np.round(np.clip(iq, -0.999, 0.999) * 32767.0).astype("<i2")
-            out.writeframes(pcm.tobytes())
+    noise = np.random.default_rng(42).normal(scale=noise_std, size=(count, 2))     # one draw for the whole capture
+    step = 2.0 * math.pi * freq_offset / sample_rate
+    with wave.open(str(path), "wb") as wav:
+        wav.setparams((2, 2, int(sample_rate), 0, "NONE", "not compressed"))
+        for lo in range(0, count, _WAV_BLOCK):
+            hi = min(count, lo + _WAV_BLOCK)
+            phase = step * np.arange(lo, hi, dtype=np.float64)
+            frame = noise[lo:hi].copy()
+            frame[:, 0] += amplitude * np.cos(phase)
+            frame[:, 1] += amplitude * np.sin(phase)
+            pcm = np.round(np.clip(frame.astype(np.float32), -0.999, 0.999) * 32767.0)
+            wav.writeframes(pcm.astype("<i2").tobytes())
     return count
 
 
-def run_benchmark(*, seconds: float, sample_rate: float, freq_offset: float, center_freq: float | None,
-                  target_freq: float | None, base_kwargs: Mapping[str, object] | None) -> int:
+def _check_request(seconds: float, sample_rate: float, freq_offset: float) -> None:
     if seconds <= 0:
         raise ValueError("Benchmark duration must be positive.")
     if sample_rate <= 0:
         raise ValueError("Benchmark sample rate must be positive.")
-    if abs(freq_offset) >= sample_rate / 2.0:
+    if abs(freq_offset) >= 0.5 * sample_rate:
         raise ValueError("Benchmark offset must be within half the sample rate.")
-    mode = (base_kwargs or {}).get("demod_mode")
-    mode = mode.lower() if isinstance(mode, str) else "nfm"
-    if center_freq is not None and target_freq is not None:
-        offset = target_freq - center_freq
-    elif center_freq is not None:
-        target_freq, offset = center_freq + freq_offset, freq_offset
-    elif target_freq is not None:
-        center_freq, offset = target_freq - freq_offset, freq_offset
-    else:
-        center_freq = 400_000_000.0
-        target_freq, offset = center_freq + freq_offset, freq_offset
+
+
+def run_benchmark(*, seconds: float, sample_rate: float, freq_offset: float, center_freq: float | None,
+                  target_freq: float | None, base_kwargs: Mapping[str, object] | None) -> int:
+    _check_request(seconds, sample_rate, freq_offset)
+    options = {k: v for k, v in (base_kwargs or {}).items() if k != "target_freqs"}
+    requested_mode = options.get("demod_mode")
+    mode = requested_mode.lower() if isinstance(requested_mode, str) else "nfm"
+    tuning = _resolve_tuning(center_freq, target_freq, freq_offset)
     LOG.info("Running benchmark: %.2f s at %.2f MS/s, demod=%s, offset %.1f kHz", seconds, sample_rate / 1e6,
-             mode.upper(), offset / 1e3)
-    with tempfile.TemporaryDirectory() as tmp:
-        tmp_path = Path(tmp)
-        capture = tmp_path / f"benchmark_fc-{int(center_freq)}Hz.wav"
-        write_synthetic_capture(capture, sample_rate, seconds, offset)
-        kwargs: dict[str, Any] = dict(base_kwargs) if base_kwargs is not None else {}
-        kwargs.pop("target_freqs", None)
-        kwargs.update(target_freq=target_freq, center_freq=center_freq, center_freq_source="benchmark",
-                      demod_mode=mode, output_path=tmp_path / f"benchmark_audio_{mode}.wav", probe_only=False)
-        pipeline = ProcessingPipeline(ProcessingConfig(in_path=capture, **kwargs))
-        t0 = time.perf_counter()
-        result = pipeline.run(progress_sink=None)
-        elapsed = time.perf_counter() - t0
-    iq_samples = sample_rate * seconds
-    realtime = seconds / elapsed if elapsed > 0 else float("inf")
-    LOG.info("Benchmark processed %.0f IQ samples in %.2f s (%.2f× realtime).", iq_samples, elapsed, realtime)
+             mode.upper(), tuning.offset / 1e3)
+    with tempfile.TemporaryDirectory() as scratch:
+        scratch_dir = Path(scratch)
+        capture = scratch_dir / f"benchmark_fc-{int(tuning.center)}Hz.wav"
+        write_synthetic_capture(capture, sample_rate, seconds, tuning.offset)
+        options |= dict(target_freq=tuning.target, center_freq=tuning.center, center_freq_source="benchmark",
+                        demod_mode=mode, probe_only=False, output_path=scratch_dir / f"benchmark_audio_{mode}.wav")
+        pipeline = ProcessingPipeline(ProcessingConfig(in_path=capture, **options))
+        started = time.perf_counter()
+        outcome = pipeline.run(progress_sink=None)          # the only timed statement, as in the reference
+        elapsed = time.perf_counter() - started
+    total = sample_rate * seconds
+    speed = seconds / elapsed if elapsed > 0 else float("inf")
+    LOG.info("Benchmark processed %.0f IQ samples in %.2f s (%.2f× realtime).", total, elapsed, speed)
     LOG.info("Throughput %.1f Msamples/s end to end (file read + H2D + kernels + D2H + encode).",
-             iq_samples / max(elapsed, 1e-12) / 1e6)
-    LOG.info("Channel decimation %d -> %.1f Hz; audio peak %.2f dBFS.", result.decimation, result.fs_channel,
-             20.0 * math.log10(max(result.audio_peak, 1e-6)))
+             total / max(elapsed, 1e-12) / 1e6)
+    LOG.info("Channel decimation %d -> %.1f Hz; audio peak %.2f dBFS.", outcome.decimation, outcome.fs_channel,
+             20.0 * math.log10(max(outcome.audio_peak, 1e-6)))
     return 0
 
 
