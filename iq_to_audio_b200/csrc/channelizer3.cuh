@@ -153,8 +153,8 @@ k_channelize3(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                             xr = nr;
                             xi = ni;
                         }
-                        dst[2 * (k1 * 16) * RS] = xr;
-                        dst[2 * (k1 * 16) * RS + 1] = xi;
+                        sts64(dst + 2 * (k1 * 16) * RS, xr);
+                        sts64(dst + 2 * (k1 * 16) * RS + 1, xi);
                     });
                 }
                 named_bar_sync(1, 256);
@@ -173,8 +173,8 @@ k_channelize3(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                     pk_t* base64 = reinterpret_cast<pk_t*>(base);
                     static_for<16>([&](auto kc) {
                         constexpr int k2 = decltype(kc)::value;
-                        base64[2 * k2 * RS] = re[bitrev<16>(k2)];
-                        base64[2 * k2 * RS + 1] = im[bitrev<16>(k2)];
+                        sts64(base64 + 2 * k2 * RS, re[bitrev<16>(k2)]);
+                        sts64(base64 + 2 * k2 * RS + 1, im[bitrev<16>(k2)]);
                     });
                 }
                 mbar_arrive(t_full + s);
