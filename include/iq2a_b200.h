@@ -213,6 +213,26 @@ int  iq2a_resampler_flush(iq2a_resampler* r, int16_t* pcm, int64_t out_stride, i
 /* upper bound of the outputs a process()/flush() call can return after n_in more input samples */
 int  iq2a_resampler_max_outputs(const iq2a_resampler* r, int64_t n_in, int64_t* n_out);
 
+/* ---- spectrum previews: what spectrum.py computes for the interactive front end, in float64 on the device.
+ *      Frames are raw interleaved PCM (codec / iq_order as for the bank); complex64 input is codec F32, order IQ.
+ *      nfft must be a power of two (the front end offers 65536 ... 524288, interactive/panels.py:238). ---- */
+/* compute_psd (spectrum.py:15-45): Hann window over min(n_frames, nfft) samples, zero padded to nfft, fft-shifted
+ * dBFS/Hz into psd_db[nfft].  The frequency axis is fftshift(fftfreq(nfft, 1/fs)), left to the caller. */
+int  iq2a_psd(const void* raw, int64_t n_frames, int32_t codec, int32_t iq_order, int32_t nfft,
+              double sample_rate, double* psd_db, int32_t device);
+/* streaming_waterfall (spectrum.py:54-92): push() feeds one chunk of the stream (host memory), every complete
+ * nfft-window at stride hop (hop <= 0: nfft/4) is transformed, added to the running mean and appended to the
+ * slice list, which is halved by pair averaging whenever it exceeds max_slices (spectrum.py:174-208).
+ * result(): avg_psd_db[nfft] float64, times[n_slices] float32 (seconds), matrix[n_slices][nfft] float32;
+ * any of them may be NULL.  With no complete window it fails like the reference's ValueError. */
+typedef struct iq2a_spectrum iq2a_spectrum;
+int  iq2a_spectrum_create(int32_t nfft, int32_t hop, int32_t max_slices, double sample_rate, int32_t codec,
+                          int32_t iq_order, int32_t device, iq2a_spectrum** out);
+void iq2a_spectrum_destroy(iq2a_spectrum* s);
+int  iq2a_spectrum_push(iq2a_spectrum* s, const void* raw, int64_t n_frames);
+int  iq2a_spectrum_counts(const iq2a_spectrum* s, int64_t* frames, int32_t* n_slices, int64_t* launches);
+int  iq2a_spectrum_result(iq2a_spectrum* s, double* avg_psd_db, float* times, float* matrix);
+
 #ifdef __cplusplus
 }
 #endif

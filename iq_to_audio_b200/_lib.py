@@ -32,6 +32,8 @@ SYMBOLS = (
     "iq2a_unpack_mix", "iq2a_fir", "iq2a_decimate", "iq2a_demod", "iq2a_scan",
     "iq2a_resampler_create", "iq2a_resampler_destroy", "iq2a_resampler_process", "iq2a_resampler_flush",
     "iq2a_resampler_max_outputs",
+    "iq2a_psd", "iq2a_spectrum_create", "iq2a_spectrum_destroy", "iq2a_spectrum_push", "iq2a_spectrum_counts",
+    "iq2a_spectrum_result",
 )
 
 
@@ -110,9 +112,16 @@ def load() -> C.CDLL:
     lib.iq2a_resampler_process.argtypes = [vp, fp, i64, i64, fp, i64, C.POINTER(i64)]
     lib.iq2a_resampler_flush.argtypes = [vp, fp, i64, C.POINTER(i64)]
     lib.iq2a_resampler_max_outputs.argtypes = [vp, i64, C.POINTER(i64)]
+    lib.iq2a_psd.argtypes = [vp, i64, i32, i32, i32, f64, fp, i32]
+    lib.iq2a_spectrum_create.argtypes = [i32, i32, i32, f64, i32, i32, i32, C.POINTER(vp)]
+    lib.iq2a_spectrum_destroy.argtypes = [vp]
+    lib.iq2a_spectrum_destroy.restype = None
+    lib.iq2a_spectrum_push.argtypes = [vp, vp, i64]
+    lib.iq2a_spectrum_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64)]
+    lib.iq2a_spectrum_result.argtypes = [vp, fp, fp, fp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("iq2a_last_error", "iq2a_bank_destroy", "iq2a_resampler_destroy"):
+        if name not in ("iq2a_last_error", "iq2a_bank_destroy", "iq2a_resampler_destroy", "iq2a_spectrum_destroy"):
             fn.restype = C.c_int
     _lib = lib
     return lib
