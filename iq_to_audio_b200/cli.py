@@ -32,7 +32,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--bw", dest="bandwidth", type=positive_float, default=12_500.0)
     p.add_argument("--fc", dest="center_freq", type=positive_float)
     p.add_argument("--fs-ch", dest="fs_ch", type=positive_float, default=96_000.0)
-    p.add_argument("--demod", dest="demod", choices=["nfm", "am", "usb", "lsb", "ssb"], default="nfm")
+    p.add_argument("--demod", dest="demod", choices=["nfm", "am", "usb", "lsb", "ssb", "none"], default="nfm")
     p.add_argument("--deemph", dest="deemph_us", type=positive_float, default=300.0)
     p.add_argument("--no-agc", dest="agc_enabled", action="store_false")
     p.add_argument("--out", dest="output_path", type=Path)

@@ -12,8 +12,10 @@ PCM bytes (the sample-format conversion and IQ order fix happen on the GPU), so 
 ffmpeg subprocess is not needed for WAV/raw inputs.  The encode side is unchanged: float32 audio is
 piped to ffmpeg for the 48 kHz resample + PCM_16 encode when ffmpeg is available.
 
-Out of scope here: metadata sniffing via ffprobe/soundfile, stage plots,
-pass-through slice writers, the GUI.
+Pass-through (`demod_mode` none/pass/iq) writes the channelised IQ with `IQSliceWriter` in the
+capture's own container and sample format (processing.py:542-596, :1114-1121).
+
+Out of scope here: metadata sniffing via ffprobe/soundfile, stage plots, the GUI.
 """
 from __future__ import annotations
 
@@ -350,6 +352,89 @@ class AudioWriter:
 
 
 # ------------------------------------------------------------------------------------------
+# pass-through output: channelised IQ in the capture's own container / sample format
+# ------------------------------------------------------------------------------------------
+def encode_iq_frames(samples: np.ndarray, codec: str) -> bytes:
+    """complex64 -> interleaved PCM frames, the raw-file rule of the reference (processing.py:527-539):
+    f32 as is; s16 = trunc(clip(x, -1, 0.999969) * 32767); u8 = round((clip(x, -1, 1) + 1) * 127.5)."""
+    pairs = np.ascontiguousarray(samples, dtype=np.complex64).view(np.float32)
+    if codec == "pcm_f32le":
+        return pairs.astype("<f4", copy=False).tobytes()
+    if codec == "pcm_s16le":
+        return (np.clip(pairs, -1.0, 0.999969) * 32767.0).astype("<i2").tobytes()
+    if codec == "pcm_u8":
+        return np.round((np.clip(pairs, -1.0, 1.0) + 1.0) * 127.5).astype(np.uint8).tobytes()
+    raise ValueError(f"Unsupported raw codec {codec}")
+
+
+def _sndfile_frames(samples: np.ndarray, codec: str) -> bytes:
+    """What libsndfile stores when float32 frames are written to a PCM_16 / PCM_U8 / FLOAT WAV with its default
+    settings (normalisation on, clipping off): lrintf(x * 0x7FFF) resp. lrintf(x * 0x7F) + 128, wrapping on
+    overflow.  (soundfile is not installable in the build image: this conversion is restated from libsndfile's
+    pcm.c, not pinned against it.)"""
+    pairs = np.ascontiguousarray(samples, dtype=np.complex64).view(np.float32)
+    if codec == "pcm_f32le":
+        return pairs.astype("<f4", copy=False).tobytes()
+    if codec == "pcm_s16le":
+        return (np.rint(pairs * np.float32(32767.0)).astype(np.int64) & 0xFFFF).astype("<u2").tobytes()
+    if codec == "pcm_u8":
+        return ((np.rint(pairs * np.float32(127.0)).astype(np.int64) + 128) & 0xFF).astype(np.uint8).tobytes()
+    raise ValueError(f"Unsupported WAV codec for slices: {codec}")
+
+
+class IQSliceWriter:
+    """ref: processing.py:542-596.  Writes the decimated channel as 2-channel IQ, WAV when the capture was a WAV
+    (same sample format), headerless frames otherwise; tracks the peak magnitude."""
+
+    _WAV_FORMATS = {"pcm_u8": (1, 8), "pcm_s16le": (1, 16), "pcm_f32le": (3, 32)}
+
+    def __init__(self, output_path: Path, sample_rate: float, spec: "InputFormat"):
+        self.output_path = Path(output_path)
+        self.sample_rate = float(sample_rate)
+        self.spec = spec
+        self.peak = 0.0
+        self._bytes = 0
+        if spec.container == "wav" and spec.codec not in self._WAV_FORMATS:
+            raise ValueError(f"Unsupported WAV codec for slices: {spec.codec}")
+        self._fd = self.output_path.open("wb")
+        if spec.container == "wav":
+            self._fd.write(self._header(0))
+
+    def _header(self, data_bytes: int) -> bytes:
+        tag, bits = self._WAV_FORMATS[self.spec.codec]
+        rate = max(1, int(round(self.sample_rate)))
+        block = 2 * bits // 8
+        fmt = struct.pack("<HHIIHH", tag, 2, rate, rate * block, block, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt
+        if tag == 3:
+            body += b"fact" + struct.pack("<II", 4, min(data_bytes // block, 0xFFFFFFFF))
+        body += b"data" + struct.pack("<I", min(data_bytes, 0xFFFFFFFF))
+        return b"RIFF" + struct.pack("<I", min(len(body) + data_bytes, 0xFFFFFFFF)) + body
+
+    def write(self, samples: np.ndarray) -> None:
+        if samples.size == 0:
+            return
+        peak = float(np.max(np.abs(samples)))
+        if peak > self.peak:
+            self.peak = peak
+        if self.spec.container == "wav":
+            payload = _sndfile_frames(samples, self.spec.codec)
+        else:
+            payload = encode_iq_frames(samples, self.spec.codec)
+        self._fd.write(payload)
+        self._bytes += len(payload)
+
+    def close(self) -> None:
+        if self._fd is None:
+            return
+        if self.spec.container == "wav":
+            self._fd.seek(0)
+            self._fd.write(self._header(self._bytes))
+        self._fd.close()
+        self._fd = None
+
+
+# ------------------------------------------------------------------------------------------
 _FREQ_IN_NAME = re.compile(r"(?<![0-9.])(\d{5,11})\s*hz", re.IGNORECASE)
 
 
@@ -407,14 +492,33 @@ class ProcessingPipeline:
         if self._cancelled:
             raise ProcessingCancelled(f"Processing cancelled during {where}.")
 
-    # reference: processing.py:1214-1233
-    def _default_output_path(self, freq: float) -> Path:
-        return self.config.in_path.with_name(f"audio_{int(freq)}_48k.wav")
+    def _is_pass_through_mode(self) -> bool:                      # reference: processing.py:693-695
+        return (self.config.demod_mode or "").lower() in {"none", "pass", "iq"}
 
-    def _output_for(self, freq: float, total: int) -> Path:
+    # reference: processing.py:1214-1233
+    def _default_output_path(self, freq: float, fmt: "InputFormat | None" = None) -> Path:
+        in_path = Path(self.config.in_path)
+        if self._is_pass_through_mode():
+            suffix = in_path.suffix
+            if fmt is not None and fmt.container == "wav":
+                ext = suffix if suffix.lower() in {".wav", ".wave", ".wv", ".rf64"} else ".wav"
+            elif fmt is not None and fmt.container == "raw":
+                ext = suffix or {"pcm_u8": ".cu8", "pcm_s16le": ".cs16", "pcm_f32le": ".cf32"}.get(fmt.codec, ".raw")
+            else:
+                ext = suffix or ".wav"
+            return in_path.with_name(f"slice_{int(freq)}{ext}")
+        return in_path.with_name(f"audio_{int(freq)}_48k.wav")
+
+    @staticmethod
+    def _annotate(base: Path | None, freq: float, total: int) -> Path | None:       # cli.py:523-527
+        if base is None or total <= 1:
+            return None if base is None else Path(base)
+        return Path(base).with_name(f"{Path(base).stem}_{int(round(freq))}{Path(base).suffix}")
+
+    def _output_for(self, freq: float, total: int, fmt: "InputFormat | None" = None) -> Path:
         base = self.config.output_path
         if base is None:
-            return self._default_output_path(freq)
+            return self._default_output_path(freq, fmt)
         if total <= 1:
             return Path(base)
         return Path(base).with_name(f"{Path(base).stem}_{int(round(freq))}{Path(base).suffix}")   # cli.py:523-527
@@ -469,9 +573,10 @@ class ProcessingPipeline:
         prog = _Progress(progress_sink, {"ingest": total_in, "channel": total_in / decimation,
                                          "demod": total_in / decimation,
                                          "encode": total_in / sample_rate * 48_000.0})
-        outputs = [self._output_for(f, len(targets)) for f in targets]
-        writers: list[AudioWriter] = []
-        dump = None
+        pass_through = self._is_pass_through_mode()
+        outputs = [self._output_for(f, len(targets), fmt) for f in targets]
+        writers: list = []
+        dumps: list = []
         results: list[ProcessingResult] = []
         processed = 0
         try:
@@ -502,9 +607,13 @@ class ProcessingPipeline:
                                    [Target(f - center, taps, s, cfg.demod_mode, cfg.deemph_us, cfg.agc_enabled)
                                     for f, s in zip(targets, signs)],
                                    codec=fmt.codec, iq_order=cfg.iq_order, ref_chunk=chunk, device=cfg.device)
-                writers = [AudioWriter(o, fs_channel) for o in outputs]
-                if cfg.dump_iq_path:
-                    dump = Path(cfg.dump_iq_path).open("wb")
+                if pass_through:                                   # processing.py:1014-1015
+                    writers = [IQSliceWriter(o, fs_channel, fmt) for o in outputs]
+                else:
+                    writers = [AudioWriter(o, fs_channel) for o in outputs]
+                if cfg.dump_iq_path:                               # one cf32 dump per target (cli.py:623, :666)
+                    dumps = [self._annotate(Path(cfg.dump_iq_path), f, len(targets)).open("wb") for f in targets]
+                want_bb = pass_through or bool(dumps)
 
                 def blocks():
                     nonlocal processed
@@ -524,20 +633,28 @@ class ProcessingPipeline:
                         blk = reader.read_raw_block(left)
 
                 with bank:
-                    for res in bank.stream(blocks(), want_baseband=dump is not None, want_audio=False):
+                    for res in bank.stream(blocks(), want_baseband=want_bb, want_audio=False,
+                                           want_clipped=not pass_through):
                         prog.advance("channel", float(res.count))
-                        if dump is not None:                        # --dump-iq: channelized cf32 (first target)
-                            dump.write(res.baseband[0].tobytes())
+                        for fd, row in zip(dumps, res.baseband if dumps else ()):   # IQDebugWriter, :363-378
+                            fd.write(row.tobytes())
                         prog.advance("demod", float(res.count))
-                        for w, row in zip(writers, res.clipped):
-                            w.write_clipped(row)
+                        if pass_through:                            # processing.py:1114-1121
+                            for w, row in zip(writers, res.baseband):
+                                w.write(row)
+                        else:
+                            for w, row in zip(writers, res.clipped):
+                                w.write_clipped(row)
                         self._check_cancel("encode")
                         prog.advance("encode", res.count / max(fs_channel, 1e-9) * 48_000.0)
-                    peaks = bank.peaks
+                    peaks = [w.peak for w in writers] if pass_through else bank.peaks
             for w, pk in zip(writers, peaks):
                 w.peak = pk
             for f, s, o, pk in zip(targets, signs, outputs, peaks):
-                LOG.info("Audio peak level %.2f dBFS.", 20.0 * math.log10(max(pk, 1e-6)))
+                if pass_through:
+                    LOG.info("IQ slice peak magnitude %.2f dBFS (complex).", 20.0 * math.log10(max(pk, 1e-6)))
+                else:
+                    LOG.info("Audio peak level %.2f dBFS.", 20.0 * math.log10(max(pk, 1e-6)))
                 results.append(ProcessingResult(probe, center, f, f - center, decimation, fs_channel, s, pk, o, processed))
             return results
         except ProcessingCancelled:
@@ -556,6 +673,6 @@ class ProcessingPipeline:
         finally:
             for w in writers:
                 w.close()
-            if dump is not None:
-                dump.close()
+            for fd in dumps:
+                fd.close()
             prog.close()

@@ -145,3 +145,61 @@ def test_gpu_resampler_matches_libswresample_vectors(key, pieces):
     assert np.abs(got[1].astype(np.int64) + got[0].astype(np.int64)).max() <= 1   # odd symmetry up to rounding ties
     with pytest.raises(ValueError):
         Resampler48k(48_000, 1)
+
+
+def test_pass_through_writes_iq_slices_wav(tmp_path):
+    # --demod none (processing.py:693-695, :1114-1121): the channelised IQ of every target, in the capture's own
+    # container and sample format, plus one cf32 debug dump per target (cli.py:623)
+    from iq_to_audio_b200.pipeline import ProcessingConfig, ProcessingPipeline
+    m = _cases.manifest()["case_b_nfm_10M"]
+    cap = tmp_path / "baseband_100000000Hz_capture.wav"
+    _write_wav(cap, _cases.raw_input("case_b_nfm_10M"), m["fs"])
+    fc = 100_000_000.0
+    cfg = ProcessingConfig(in_path=cap, target_freqs=[fc + t["f_off"] for t in m["targets"]], target_freq=fc,
+                           chunk_size=m["chunk"], mix_sign_override=1, demod_mode="none",
+                           dump_iq_path=tmp_path / "dbg.cf32")
+    res = ProcessingPipeline(cfg).run_many()
+    assert len(res) == 5
+    for i, r in enumerate(res):
+        g = _cases.load(f"case_b_nfm_10M_t{i}")
+        bb = g["baseband"]
+        assert r.output_path.name == f"slice_{int(r.target_freq)}.wav"           # processing.py:1216-1232
+        with wave.open(str(r.output_path), "rb") as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (2, 2, 96_154)
+            got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.int64)
+        want = np.rint(bb.view(np.float32).astype(np.float64) * 32767.0).astype(np.int64)
+        assert got.size == want.size
+        assert np.max(np.abs(got - want)) <= 1
+        assert abs(r.audio_peak - float(np.max(np.abs(bb)))) < 1e-5
+        dbg = np.fromfile(tmp_path / f"dbg_{int(round(r.target_freq))}.cf32", dtype=np.complex64)
+        assert dbg.size == bb.size and np.max(np.abs(dbg - bb)) < 2e-6
+
+
+@pytest.mark.parametrize("suffix,codec", [(".cs16", "pcm_s16le"), (".cu8", "pcm_u8"), (".cf32", "pcm_f32le")])
+def test_pass_through_raw_containers(tmp_path, suffix, codec):
+    from iq_to_audio_b200.pipeline import ProcessingConfig, ProcessingPipeline
+    m = _cases.manifest()["case_a_nfm_2p5M"]
+    raw16 = _cases.raw_input("case_a_nfm_2p5M")
+    x = raw16.astype(np.float64) / 32768.0
+    raw = {"pcm_s16le": raw16, "pcm_u8": orc.to_u8(x.reshape(-1, 2)), "pcm_f32le": x.astype(np.float32)}[codec]
+    cap = tmp_path / f"capture_433000000Hz{suffix}"
+    raw.tofile(cap)
+    cfg = ProcessingConfig(in_path=cap, target_freq=433_000_000.0 + m["targets"][0]["f_off"], chunk_size=m["chunk"],
+                           mix_sign_override=1, demod_mode="pass", input_sample_rate=m["fs"])
+    r = ProcessingPipeline(cfg).run()
+    assert r.output_path.name == f"slice_{int(r.target_freq)}{suffix}"
+    # what the reference stages produce from the same frames (oracle), then its raw encoding rule (:527-539)
+    xin = orc.order_iq(orc.unpack_interleaved(raw, codec), "iq")
+    plan = orc.TargetPlan(m["fs"], m["targets"][0]["f_off"], m["targets"][0]["bw"], "nfm", mix_sign=1)
+    bb = orc.run_target(xin, plan, chunk=1 << 20).baseband.view(np.float32).astype(np.float64)
+    data = np.fromfile(r.output_path, dtype={"pcm_s16le": "<i2", "pcm_u8": np.uint8, "pcm_f32le": "<f4"}[codec])
+    assert data.size == bb.size
+    if codec == "pcm_s16le":
+        want = (np.clip(bb, -1.0, 0.999969) * 32767.0).astype(np.int64)          # truncation, as astype does
+        assert np.max(np.abs(data.astype(np.int64) - want)) <= 1
+    elif codec == "pcm_u8":
+        want = np.round((np.clip(bb, -1.0, 1.0) + 1.0) * 127.5).astype(np.int64)
+        assert np.max(np.abs(data.astype(np.int64) - want)) <= 1
+    else:
+        assert np.max(np.abs(data.astype(np.float64) - bb)) < 2e-6
+    assert abs(r.audio_peak - float(np.max(np.abs(bb.view(np.complex128))))) < 1e-5

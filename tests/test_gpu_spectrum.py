@@ -118,3 +118,67 @@ def test_silence_hits_the_floor():
     from iq_to_audio_b200.spectrum import compute_psd
     _, psd = compute_psd(np.zeros(5000, np.complex64), 1e6, 4096)
     np.testing.assert_array_equal(psd, np.full(4096, -180.0))
+
+
+def _capture(tmp_path):
+    import wave
+    from tests import _cases
+    raw = _cases.raw_input("case_b_nfm_10M")
+    cap = tmp_path / "baseband_100000000Hz_capture.wav"
+    with wave.open(str(cap), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(10_000_000)
+        w.writeframes(raw.tobytes())
+    return cap, orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "qi")
+
+
+def test_gather_snapshot_matches_reference_flow(tmp_path):
+    # interactive/workers.py:36-161: first `seconds` of the capture, raw frames straight to the device
+    from iq_to_audio_b200.pipeline import ProcessingConfig
+    from iq_to_audio_b200.preview import gather_snapshot
+    cap, x = _capture(tmp_path)
+    calls = []
+    snap = gather_snapshot(ProcessingConfig(in_path=cap, iq_order="qi"), 0.05, nfft=65536, hop=None, max_slices=4,
+                           max_in_memory_samples=100_000, progress_cb=lambda s, f: calls.append((s, f)))
+    use = x[:500_000]
+    o_avg, o_t, o_m, o_frames = so.waterfall([use], 10e6, 65536, None, 4)
+    assert snap.fft_frames == o_frames and snap.mode == "samples" and snap.center_freq == 100e6
+    assert snap.seconds == 0.05 and snap.sample_rate == 10e6 and calls[-1] == (0.05, 1.0)
+    np.testing.assert_array_equal(snap.samples, use[:100_000])
+    np.testing.assert_allclose(snap.psd_db, o_avg, rtol=0, atol=DB_TOL)
+    f, t, mat = snap.waterfall
+    np.testing.assert_array_equal(t, o_t)
+    np.testing.assert_allclose(mat, o_m, rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(f, so.freq_axis(65536, 10e6))
+
+
+def test_compute_full_psd_ragged_chunks(tmp_path):
+    # interactive/workers.py:164-287: whole recording, chunk = max(config.chunk_size, nfft)
+    from iq_to_audio_b200.pipeline import ProcessingConfig
+    from iq_to_audio_b200.preview import compute_full_psd
+    cap, _ = _capture(tmp_path)
+    x = orc.order_iq(orc.unpack_interleaved(__import__("tests._cases", fromlist=["x"]).raw_input("case_b_nfm_10M"),
+                                            "pcm_s16le"), "iq")
+    msgs = []
+    snap = compute_full_psd(ProcessingConfig(in_path=cap, chunk_size=150_001), nfft=32768, hop=10_000, max_slices=16,
+                            status_cb=msgs.append)
+    chunks = [x[i:i + 150_001] for i in range(0, x.size, 150_001)]
+    o_avg, o_t, o_m, o_frames = so.waterfall(chunks, 10e6, 32768, 10_000, 16)
+    assert snap.fft_frames == o_frames and snap.samples is None and snap.params["full_capture"] is True
+    assert msgs[0].startswith("Reading full recording") and any("Averaging PSD chunk" in m for m in msgs)
+    np.testing.assert_array_equal(snap.waterfall[1], o_t)
+    np.testing.assert_allclose(snap.psd_db, o_avg, rtol=0, atol=DB_TOL)
+    np.testing.assert_allclose(snap.waterfall[2], o_m, rtol=0, atol=2e-5)
+
+
+def test_preview_errors(tmp_path):
+    from iq_to_audio_b200.pipeline import ProcessingConfig
+    from iq_to_audio_b200.preview import gather_snapshot
+    raw = tmp_path / "cap.cs16"
+    raw.write_bytes(np.zeros(4000, np.int16).tobytes())
+    with pytest.raises(ValueError, match="sample rate override"):
+        gather_snapshot(ProcessingConfig(in_path=raw, center_freq=1e6), 1.0, nfft=1024, hop=None, max_slices=4)
+    with pytest.raises(ValueError, match="Center frequency"):
+        gather_snapshot(ProcessingConfig(in_path=raw, input_sample_rate=1e6), 1.0, nfft=1024, hop=None, max_slices=4)
+    with pytest.raises(ValueError, match="enough samples"):
+        gather_snapshot(ProcessingConfig(in_path=raw, input_sample_rate=1e6, center_freq=1e6), 1.0, nfft=4096,
+                        hop=None, max_slices=4)
