@@ -3,8 +3,9 @@
 Only the flags that reach the channelize-and-demodulate path are kept (`--in --ft --bw --fc --fs-ch
 --demod --deemph --no-agc --out --dump-iq --chunk --filter-block --iq-order --mix-sign
 --input-format --input-sample-rate --preview --probe-only --benchmark*`); the GUI, squelch and
-digital-decoder flags belong to subsystems outside the scope table.  All `--ft` targets (up to the
-reference's five, cli.py:514-515) run as ONE pass over the capture."""
+digital-decoder flags belong to subsystems outside the scope table.  All `--ft` targets run as ONE pass over
+the capture; the reference's limit of five per run (cli.py:514-515, there because every target is another full
+pass) becomes MAX_TARGETS, the 256 channels of the wideband sweep configuration."""
 from __future__ import annotations
 
 import argparse
@@ -55,13 +56,16 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
+MAX_TARGETS = 256
+
+
 def main(argv: list[str] | None = None) -> int:
     parser = build_parser()
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO, format="%(levelname)s %(message)s")
     freqs = list(args.target_freqs or [])
-    if len(freqs) > 5:
-        parser.error("At most five target frequencies are supported per run.")
+    if len(freqs) > MAX_TARGETS:
+        parser.error(f"At most {MAX_TARGETS} target frequencies are supported per run.")
     for i, f in enumerate(freqs):
         if any(math.isclose(f, g, rel_tol=0.0, abs_tol=0.5) for g in freqs[:i]):
             parser.error("Duplicate target frequencies are not allowed.")

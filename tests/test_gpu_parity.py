@@ -441,3 +441,31 @@ def test_cfg4_cfg5_shapes_against_oracle(gpu):
         assert audio.shape[1] == want.audio.size == orc.decimated_count(0, n, d)
         assert np.abs(bb[i] - want.baseband).max() <= BB_TOL
         assert np.abs(audio[i] - want.audio).max() <= AUDIO_TOL
+
+
+def test_cfg5_256_channels(gpu):
+    """The widest bank of the sweep configuration: 256 NFM channels at 61.44 MS/s in one pass (32 launch groups
+    of 8 sharing the capture in L2).  Three channels against the oracle, and the lifted CLI cap's bound."""
+    fs = 61.44e6
+    d, _ = orc.plan_decimation(fs, 96_000.0)
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    n = 1_200_000
+    offs = [(-29.0 + 58.0 * i / 255.0) * 1e6 for i in range(256)]
+    pick = (0, 131, 255)
+    carriers = [dict(offset=offs[i], amp=0.2, kind="fm", tone=500.0 + 150.0 * j, dev=2500.0) for j, i in enumerate(pick)]
+    raw = orc.to_s16(orc.multi_carrier_capture(fs, n, carriers, noise_std=0.01, seed=9))
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    chunk = 1 << 20
+    T = gpu["Target"]
+    with gpu["ChannelBank"](fs, d, [T(o, taps, 1, "nfm") for o in offs], ref_chunk=chunk) as bank:
+        assert bank.n_channels == 256
+        parts = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, n)], want_baseband=True) for s in range(0, n, chunk)]
+        audio = np.concatenate([p.audio for p in parts], axis=1)
+        bb = np.concatenate([p.baseband for p in parts], axis=1)
+    assert audio.shape == (256, orc.decimated_count(0, n, d))
+    for i in pick:
+        want = orc.run_target(x, orc.TargetPlan(sample_rate=fs, freq_offset=offs[i], mix_sign=1), chunk)
+        assert np.abs(bb[i] - want.baseband).max() <= BB_TOL
+        assert np.abs(audio[i] - want.audio).max() <= AUDIO_TOL
+    with pytest.raises(ValueError, match="n_channels"):
+        gpu["ChannelBank"](fs, d, [T(o, taps, 1, "nfm") for o in offs + [1.0]], ref_chunk=chunk)

@@ -95,8 +95,10 @@ def test_cli_benchmark_surface(no_ffmpeg, caplog):
     assert rc == 0
     assert any("Benchmark processed 1250000 IQ samples" in r.getMessage() for r in caplog.records)
     assert cli.main(["--benchmark", "--benchmark-offset", "2000000"]) == 1        # offset beyond fs/2 -> error exit
-    with pytest.raises(SystemExit):
-        cli.main(["--ft", "1", "--ft", "2", "--ft", "3", "--ft", "4", "--ft", "5", "--ft", "6", "--in", "x.wav"])
+    with pytest.raises(SystemExit):                                               # duplicate targets (cli.py:516-519)
+        cli.main(["--ft", "1000", "--ft", "1000.2", "--in", "x.wav"])
+    with pytest.raises(SystemExit):                                               # the cap is the bank's, not five
+        cli.main(sum((["--ft", str(1000 + 10 * i)] for i in range(cli.MAX_TARGETS + 1)), []) + ["--in", "x.wav"])
 
 
 def test_pipeline_errors(tmp_path, no_ffmpeg):
