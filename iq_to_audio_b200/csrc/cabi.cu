@@ -104,6 +104,7 @@ struct iq2a_bank {
     iq2a_bank_config cfg{};
     int C = 0, D = 1, M = 0, R1 = 32, vd = 0, ld = 0, n_sm = 148;
     bool any_agc = false;
+    int64_t tail_fused_w = 0;   // > 0: the single-pass tail applies (tail.cuh)
     std::vector<std::vector<double>> taps;
     std::vector<int64_t> tap_off;   // offsets of each channel's taps in d_taps
     std::vector<int> modes;
@@ -387,6 +388,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     t.dc_radius = 0.995;                          // decoders/common.py:9
     t.agc_target = std::pow(10.0, -12.0 / 20.0);  // decoders/ssb.py:21,33
     t.agc_decay = 0.001;                          // decoders/ssb.py:22
+    t.fused_w = b->tail_fused_w;
     if ((rc = launch_tail(t, b->any_agc, a.st, &b->launches))) return rc;
     if (!b->precise.empty()) {
         if ((rc = dev_grow(&b->d_tmp, &b->tmp_cap, (size_t)C * stride))) return rc;
@@ -617,6 +619,20 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         ok &= cudaMemset(b->d_repaired, 0, sizeof(int)) == cudaSuccess;
     }
     if (!ok) { cudaFree(d_wtab); set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(IQ2A_ERR_CUDA); }
+    {
+        // single-pass tail: every channel a constant-pole recurrence (NFM de-emphasis; AM / SSB-without-AGC DC blocker)
+        const char* env = std::getenv("IQ2A_TAIL");
+        int64_t w = (env && std::strcmp(env, "v1") == 0) ? 0 : 1;
+        for (int c = 0; c < C && w > 0; ++c) {
+            const int m = tc[c].mode;
+            int64_t rows = 0;
+            if (tc[c].precise || b->any_agc) rows = 0;
+            else if (m == IQ2A_MODE_NFM) rows = tail_memory_rows(tc[c].alpha);
+            else if (m == IQ2A_MODE_AM || m == IQ2A_MODE_USB || m == IQ2A_MODE_LSB) rows = tail_memory_rows(0.995);
+            w = rows > 0 ? std::max(w, rows) : 0;
+        }
+        b->tail_fused_w = w;
+    }
     {
         const char* env = std::getenv("IQ2A_CHANNELIZER");
         const bool force_v1 = env && std::strcmp(env, "v1") == 0;

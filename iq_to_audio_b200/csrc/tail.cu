@@ -19,6 +19,9 @@
 // channel), per-tile apply.  All in float64: the reference runs the de-emphasis in
 // float64 (lfilter) and the DC blocker / AGC as float32 sequential loops; float64 scans
 // differ from those by < 1e-5 pre-clip, well inside the 1e-4 tolerance.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 #include "tail.cuh"
 #include "../../include/iq2a_b200.h"
@@ -301,6 +304,171 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TailParams p,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// single-pass tail for constant-pole recurrences (NFM de-emphasis, AM / SSB-without-AGC DC blocker)
+// ---------------------------------------------------------------------------------------
+// v[m] = a v[m-1] + b[m] with |a| < 1 forgets: a^W < 1e-18 means rows more than W back cannot change v[m] in
+// float64.  So a CTA that owns rows [t0, t1) starts W rows early from zero state (from the carried state when
+// that reaches row 0), walks forward in 1024-row steps and is exact to rounding without any communication between
+// CTAs: no aggregate pass, no carry pass, and the detector output never goes to memory.  Per step: detector
+// (atan2 / hypot / real part) on 4 consecutive rows per thread, thread-local recurrence, warp + block prefix with
+// the constant multipliers a^4, a^8, ..., a^128, emit.  Reads the channel samples once (plus W/len of them twice).
+constexpr int kFusedThreads = 256;
+constexpr int kFusedStep = kFusedThreads * 4;
+
+__device__ __forceinline__ float detect(int mode, float2 s, float2 prev) {
+    if (mode == MODE_NFM) {
+        const float re = __fmaf_rn(s.x, prev.x, __fmul_rn(s.y, prev.y));       // same form as k_pre
+        const float im = __fmaf_rn(s.x, -prev.y, __fmul_rn(s.y, prev.x));
+        return atan2f(im, re);
+    }
+    if (mode == MODE_AM) return hypotf(s.x, s.y);
+    return s.x;
+}
+
+__global__ void __launch_bounds__(kFusedThreads) k_tail_fused(const TailParams p) {
+    __shared__ double warp_tot[kFusedThreads / 32];
+    const int c = blockIdx.y;
+    const TailChan ch = p.chan[c];
+    const int kind = scan_kind(ch, 0);
+    const bool deemph = kind == SCAN_DEEMPH;
+    const double a = deemph ? ch.alpha : p.dc_radius;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // constant multipliers
+    const double a2 = a * a, a4 = a2 * a2;
+    double step_pw[5];                       // a^(4 * 2^k)
+    step_pw[0] = a4;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) step_pw[k] = step_pw[k - 1] * step_pw[k - 1];
+    const double a128 = step_pw[4] * step_pw[4];
+    double a_lane = 1.0, a_warp = 1.0;       // a^(4 lane), a^(128 wid)
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (lane & (1 << k)) a_lane *= step_pw[k];
+    {
+        double q = a128;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (wid & (1 << k)) a_warp *= q;
+            q *= q;
+        }
+    }
+    double a1024 = a128;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a1024 *= a1024;
+
+    const int64_t t0 = (int64_t)blockIdx.x * p.fused_len;
+    const int64_t t1 = min(p.n, t0 + p.fused_len);
+    const int64_t w0 = max((int64_t)0, t0 - p.fused_w);
+    const float2* bb = p.bb + (size_t)c * p.bb_stride;
+    const iq2a_channel_state st0 = p.state[c];
+
+    double v_in = 0.0;                       // state before row w0
+    if (w0 == 0 && !p.fresh) v_in = deemph ? st0.deemph_z : (double)st0.dc_y;
+
+    float peak = 0.f;
+    for (int64_t sub = w0; sub < t1; sub += kFusedStep) {
+        const int64_t r0 = sub + 4 * tid;
+        // ---- detector on rows r0 .. r0+3 (and the row before, for the differences) ----
+        float2 s[5];
+        if (r0 + 3 < p.n) {
+            const float4 u0 = *reinterpret_cast<const float4*>(bb + r0);
+            const float4 u1 = *reinterpret_cast<const float4*>(bb + r0 + 2);
+            s[1] = make_float2(u0.x, u0.y);
+            s[2] = make_float2(u0.z, u0.w);
+            s[3] = make_float2(u1.x, u1.y);
+            s[4] = make_float2(u1.z, u1.w);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[1 + i] = r0 + i < p.n ? bb[r0 + i] : make_float2(0.f, 0.f);
+        }
+        if (r0 > 0) s[0] = r0 - 1 < p.n ? bb[r0 - 1] : make_float2(0.f, 0.f);
+        else s[0] = p.fresh ? make_float2(1.f, 0.f) : make_float2(st0.prev_re, st0.prev_im);    // nfm.py:15
+        float x[5];
+#pragma unroll
+        for (int i = 1; i < 5; ++i) x[i] = detect(ch.mode, s[i], s[i - 1]);
+        double b[4];
+        if (deemph) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = a * (ch.beta * (double)x[1 + i]);          // z = alpha z + alpha beta x
+        } else {
+            // DC blocker input difference in float32 (common.py:24); the row before row 0 is the carried x
+            if (r0 > 0) x[0] = ch.mode == MODE_AM ? hypotf(s[0].x, s[0].y) : s[0].x;
+            else x[0] = p.fresh ? 0.f : st0.dc_x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = (double)__fsub_rn(x[1 + i], x[i]);
+        }
+        // ---- prefix: state before this thread's first row ----
+        double agg = b[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) agg = fma(a, agg, b[i]);
+        double inc = agg;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, 1 << k);
+            if (lane >= (1 << k)) inc = fma(step_pw[k], o, inc);
+        }
+        double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = 0.0;
+        __syncthreads();                     // previous step's readers are done with warp_tot
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        double before_warp = 0.0, all = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFusedThreads / 32; ++w) {
+            if (w == wid) before_warp = all;
+            all = fma(a128, all, warp_tot[w]);
+        }
+        double v = fma(a_lane, fma(a_warp, v_in, before_warp), exc);
+        v_in = fma(a1024, v_in, all);        // state before the next step
+        if (sub + kFusedStep <= t0) continue;                      // pure warm-up step: nothing to emit
+        // ---- emit ----
+        int64_t w_cur = -1;
+        double ss_cur = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = r0 + i;
+            const double v_new = fma(a, v, b[i]);
+            const float y = deemph ? (float)(ch.beta * (double)x[1 + i] + v) : (float)v_new;
+            v = v_new;
+            if (r == p.n - 1) {
+                // carried state after the last row; committed by k_state_tail once every CTA has read the old one
+                p.agg[(size_t)c * p.ntiles] = make_double2(v_new, (double)x[1 + i]);
+            }
+            if (r < t0 || r >= t1 || r < p.n_skip) continue;
+            const int64_t o = r - p.n_skip;
+            if (p.audio) p.audio[(size_t)c * p.out_stride + o] = y;
+            if (p.clipped) p.clipped[(size_t)c * p.out_stride + o] = fminf(fmaxf(y, -0.99f), 0.99f);   // processing.py:452
+            peak = fmaxf(peak, fabsf(y));
+            if (p.sumsq) {
+                int64_t w = ((p.mg0 + r) * (int64_t)p.decim - p.seg_origin) / p.seg_len - p.win0;
+                if (w < 0) w = 0;
+                if (w >= p.nwin) w = p.nwin - 1;
+                if (w != w_cur) {
+                    if (w_cur >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
+                    w_cur = w;
+                    ss_cur = 0.0;
+                }
+                ss_cur = fma((double)y, (double)y, ss_cur);
+            }
+        }
+        if (p.sumsq) {
+            const int64_t wz = __shfl_sync(0xffffffffu, w_cur, 0);
+            const bool uniform = __all_sync(0xffffffffu, w_cur == wz);
+            if (uniform) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss_cur += __shfl_xor_sync(0xffffffffu, ss_cur, off);
+                if (lane == 0 && wz >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + wz, ss_cur);
+            } else if (w_cur >= 0) {
+                atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, off));
+    if (lane == 0 && peak > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&p.state[c].peak), __float_as_uint(peak));
+}
+
 // carried quantities that are plain copies of the last row
 __global__ void k_state_tail(const TailParams p) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,13 +479,46 @@ __global__ void k_state_tail(const TailParams p) {
         p.state[c].prev_re = last.x;
         p.state[c].prev_im = last.y;
     }
+    const bool dc_mode = mode == MODE_AM || mode == MODE_USB || mode == MODE_LSB || mode == MODE_RAW_DC;
+    if (p.fused_w > 0) {
+        // k_tail_fused left (state after the last row, detector output of the last row) in agg[c][0]
+        const double2 e = p.agg[(size_t)c * p.ntiles];
+        if (dc_mode) {
+            p.state[c].dc_y = (float)e.x;
+            p.state[c].dc_x = (float)e.y;
+        } else {
+            p.state[c].deemph_z = e.x;
+        }
+        return;
+    }
     // (channels on the sequential path update their DC-blocker state themselves, after reading it)
-    if (!p.chan[c].precise && (mode == MODE_AM || mode == MODE_USB || mode == MODE_LSB || mode == MODE_RAW_DC))
-        p.state[c].dc_x = p.pre[(size_t)c * p.work_stride + p.n - 1];
+    if (!p.chan[c].precise && dc_mode) p.state[c].dc_x = p.pre[(size_t)c * p.work_stride + p.n - 1];
 }
 
-int launch_tail(const TailParams& p, bool any_agc, cudaStream_t st, int64_t* launches) {
-    if (p.n <= 0) return IQ2A_OK;
+int64_t tail_memory_rows(double pole) {
+    if (!(pole > 0.0) || !(pole < 1.0)) return pole == 0.0 ? 1024 : 0;
+    const double rows = std::ceil(std::log(1e-18) / std::log(pole));
+    if (rows > 65536.0) return 0;                                  // too slow a pole: use the three-kernel scan
+    return ((int64_t)rows + kFusedStep - 1) / kFusedStep * kFusedStep;
+}
+
+int launch_tail(const TailParams& p_in, bool any_agc, cudaStream_t st, int64_t* launches) {
+    if (p_in.n <= 0) return IQ2A_OK;
+    TailParams p = p_in;
+    if (p.skip_pre || any_agc) p.fused_w = 0;
+    if (p.fused_w > 0) {
+        // rows per CTA: enough CTAs to fill the machine on short calls, at most 1/8 of redundant history on long ones
+        int64_t len = (p.n * p.nchan / 296 + kFusedStep - 1) / kFusedStep * kFusedStep;
+        len = std::max(len, p.fused_w);
+        len = std::min(len, 8 * p.fused_w);
+        p.fused_len = len;
+        const dim3 grid((unsigned)((p.n + len - 1) / len), p.nchan);
+        k_tail_fused<<<grid, kFusedThreads, 0, st>>>(p);
+        k_state_tail<<<(p.nchan + 63) / 64, 64, 0, st>>>(p);
+        if (launches) *launches += 2;
+        IQ2A_CUDA_TRY(cudaGetLastError());
+        return IQ2A_OK;
+    }
     const dim3 gpre((unsigned)((p.n + 255) / 256), p.nchan);
     if (!p.skip_pre) k_pre<<<gpre, 256, 0, st>>>(p);
     const dim3 gscan((unsigned)p.ntiles, p.nchan);

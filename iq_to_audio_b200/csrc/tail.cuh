@@ -39,7 +39,13 @@ struct TailParams {
     int fresh;                 // 1: start the recurrences from zero state
     int skip_pre;              // 1: `pre` already holds real float32 input (stand-alone recurrences)
     double dc_radius, agc_target, agc_decay;
+    int64_t fused_w;           // > 0: every channel is a constant-pole recurrence; rows of history that make its
+                               // state exact to float64 (pole^fused_w < 1e-18), multiple of 1024 -> k_tail_fused
+    int64_t fused_len;         // rows per CTA on that path (set by launch_tail)
 };
+
+// rows after which a first-order recurrence with this pole has forgotten its state to below float64 resolution
+int64_t tail_memory_rows(double pole);
 
 int launch_tail(const TailParams& p, bool any_agc, cudaStream_t st, int64_t* launches);
 int64_t tail_tiles(int64_t n);

@@ -469,3 +469,41 @@ def test_cfg5_256_channels(gpu):
         assert np.abs(audio[i] - want.audio).max() <= AUDIO_TOL
     with pytest.raises(ValueError, match="n_channels"):
         gpu["ChannelBank"](fs, d, [T(o, taps, 1, "nfm") for o in offs + [1.0]], ref_chunk=chunk)
+
+
+@pytest.mark.parametrize("modes", [("nfm", "nfm", "nfm"), ("am", "usb", "nfm"), ("lsb", "am", "am")])
+def test_single_pass_tail_equals_three_kernel_scan(gpu, modes, monkeypatch):
+    """The single-pass tail (overlapped history per CTA, no inter-CTA carry) and the reduce / carry / apply scan
+    compute the same recurrences: same audio, clipped audio, peaks, statistics and carried state, for ragged
+    streaming calls (state carried across calls, calls shorter than the history window) and AGC off."""
+    fs, d = 10e6, 104
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    n = 3_000_001
+    carriers = [dict(offset=o, amp=0.2, kind=k, tone=700.0 + 100 * i, dev=2500.0)
+                for i, (o, k) in enumerate([(1.0e6, "fm"), (-2.2e6, "am"), (3.05e6, "usb")])]
+    raw = orc.to_s16(orc.multi_carrier_capture(fs, n, carriers, noise_std=0.01, seed=4))
+    T = gpu["Target"]
+    tg = [T(o, taps, 1, m, 300.0, False) for o, m in zip((1.0e6, -2.2e6, 3.05e6), modes)]
+    sizes = [1_500_000, 5, 300, 20_000, 104 * 1024, n]
+
+    def run():
+        with gpu["ChannelBank"](fs, d, tg, ref_chunk=1 << 20) as bank:
+            pos, audio, clip, rms = 0, [], [], []
+            for sz in sizes:
+                e = min(n, pos + sz)
+                if e > pos:
+                    r = bank.process_chunk(raw[2 * pos:2 * e])
+                    audio.append(r.audio.copy()); clip.append(r.clipped.copy()); rms.append(np.array(r.rms_dbfs))
+                pos = e
+            st, _ = bank.get_state()
+            return np.concatenate(audio, axis=1), np.concatenate(clip, axis=1), np.array(rms), bank.peaks, st, bank.launches
+    a2, c2, r2, p2, s2, l2 = run()
+    monkeypatch.setenv("IQ2A_TAIL", "v1")
+    a1, c1, r1, p1, s1, l1 = run()
+    assert l2 < l1                                             # 2 tail launches per call instead of 5
+    assert a1.shape == a2.shape == (3, orc.decimated_count(0, n, d))
+    assert np.abs(a1 - a2).max() <= 2e-7 and np.abs(c1 - c2).max() <= 2e-7
+    assert np.abs(r1 - r2).max() <= 1e-6 and np.abs(np.array(p1) - np.array(p2)).max() <= 2e-7
+    for x, y in zip(s1, s2):
+        for key in x:
+            assert abs(x[key] - y[key]) <= 1e-6 * max(1.0, abs(x[key])), key
