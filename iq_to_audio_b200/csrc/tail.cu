@@ -20,7 +20,9 @@
 // float64 (lfilter) and the DC blocker / AGC as float32 sequential loops; float64 scans
 // differ from those by < 1e-5 pre-clip, well inside the 1e-4 tolerance.
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 
 #include "common.cuh"
 #include "tail.cuh"
@@ -423,8 +425,19 @@ __global__ void __launch_bounds__(kFusedThreads) k_tail_fused(const TailParams p
         v_in = fma(a1024, v_in, all);        // state before the next step
         if (sub + kFusedStep <= t0) continue;                      // pure warm-up step: nothing to emit
         // ---- emit ----
-        int64_t w_cur = -1;
-        double ss_cur = 0.0;
+        // statistics windows are reference chunks (tens of thousands of rows): a 1024-row step touches at most two.
+        // Window of the step's first row and the first row of the next window, once per step (uniform).
+        int64_t win_a = 0, split = INT64_MAX;
+        if (p.sumsq) {
+            // window(r) = clamp(((mg0 + r) decim - origin) / seg_len - win0, 0, nwin - 1), as in k_scan_apply
+            const int64_t na = (p.mg0 + sub) * (int64_t)p.decim - p.seg_origin;
+            const int64_t wa = max(max(na / p.seg_len, p.win0), (int64_t)0);
+            win_a = min(wa - p.win0, p.nwin - 1);
+            if (win_a < p.nwin - 1)      // first row whose sample index reaches chunk wa + 1
+                split = (p.seg_origin + (wa + 1) * p.seg_len + p.decim - 1) / p.decim - p.mg0;
+        }
+        const int64_t emit_lo = max(t0, p.n_skip);
+        double ss_a = 0.0, ss_b = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t r = r0 + i;
@@ -435,32 +448,24 @@ __global__ void __launch_bounds__(kFusedThreads) k_tail_fused(const TailParams p
                 // carried state after the last row; committed by k_state_tail once every CTA has read the old one
                 p.agg[(size_t)c * p.ntiles] = make_double2(v_new, (double)x[1 + i]);
             }
-            if (r < t0 || r >= t1 || r < p.n_skip) continue;
+            if (r < emit_lo || r >= t1) continue;
             const int64_t o = r - p.n_skip;
             if (p.audio) p.audio[(size_t)c * p.out_stride + o] = y;
             if (p.clipped) p.clipped[(size_t)c * p.out_stride + o] = fminf(fmaxf(y, -0.99f), 0.99f);   // processing.py:452
             peak = fmaxf(peak, fabsf(y));
-            if (p.sumsq) {
-                int64_t w = ((p.mg0 + r) * (int64_t)p.decim - p.seg_origin) / p.seg_len - p.win0;
-                if (w < 0) w = 0;
-                if (w >= p.nwin) w = p.nwin - 1;
-                if (w != w_cur) {
-                    if (w_cur >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
-                    w_cur = w;
-                    ss_cur = 0.0;
-                }
-                ss_cur = fma((double)y, (double)y, ss_cur);
-            }
+            const double yy = (double)y * (double)y;
+            if (r < split) ss_a += yy;
+            else ss_b += yy;
         }
         if (p.sumsq) {
-            const int64_t wz = __shfl_sync(0xffffffffu, w_cur, 0);
-            const bool uniform = __all_sync(0xffffffffu, w_cur == wz);
-            if (uniform) {
+            const bool straddle = sub + kFusedStep > split;                            // uniform
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) ss_cur += __shfl_xor_sync(0xffffffffu, ss_cur, off);
-                if (lane == 0 && wz >= 0) atomicAdd(p.sumsq + (size_t)c * p.nwin + wz, ss_cur);
-            } else if (w_cur >= 0) {
-                atomicAdd(p.sumsq + (size_t)c * p.nwin + w_cur, ss_cur);
+            for (int off = 16; off > 0; off >>= 1) ss_a += __shfl_xor_sync(0xffffffffu, ss_a, off);
+            if (lane == 0 && ss_a != 0.0) atomicAdd(p.sumsq + (size_t)c * p.nwin + win_a, ss_a);
+            if (straddle) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) ss_b += __shfl_xor_sync(0xffffffffu, ss_b, off);
+                if (lane == 0 && ss_b != 0.0) atomicAdd(p.sumsq + (size_t)c * p.nwin + min(win_a + 1, p.nwin - 1), ss_b);
             }
         }
     }
@@ -506,6 +511,8 @@ int launch_tail(const TailParams& p_in, bool any_agc, cudaStream_t st, int64_t* 
     if (p_in.n <= 0) return IQ2A_OK;
     TailParams p = p_in;
     if (p.skip_pre || any_agc) p.fused_w = 0;
+    // the single-pass kernel lets a 1024-row step straddle at most one statistics-window boundary
+    if (p.sumsq && p.seg_len < (int64_t)p.decim * (kFusedStep + 1)) p.fused_w = 0;
     if (p.fused_w > 0) {
         // rows per CTA: enough CTAs to fill the machine on short calls, at most 1/8 of redundant history on long ones
         int64_t len = (p.n * p.nchan / 296 + kFusedStep - 1) / kFusedStep * kFusedStep;
