@@ -387,6 +387,18 @@ def main() -> None:
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_sample": b_alg, "kernel_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1),
                 "peak_source": peak_src}
+    # second reading of the same kernel: it is FP32-issue bound, not HBM bound.  Flops per input
+    # sample of the exact algorithm: (5 log2 M forward + 8 C multiply-accumulate) per transform point, M / Ld
+    # transform points per new sample; peak = SMs x 128 FP32 lanes x 2 x SM clock measured during the run.
+    m_fft, ld = bank.fft_size, bank.rows_per_block
+    flop_per_sample = (5.0 * np.log2(m_fft) + 8.0 * len(OFFSETS)) * m_fft / ld
+    clk = clocks.summary().get("sm_mhz") or 1965
+    fp32_peak = 148 * 128 * 2 * clk * 1e6 / 1e12
+    if chan_ms > 0:
+        tf = n_in * flop_per_sample / (chan_ms * 1e-3) / 1e12
+        roofline["fp32"] = {"flop_per_sample": flop_per_sample, "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": tf / fp32_peak,
+                            "note": "all-FMA peak; the transform butterflies are adds (1 flop per lane-slot), so ~50 % is the ceiling for them"}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -124,6 +124,7 @@ struct iq2a_bank {
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     bool v2_ok = false;
+    bool cp_ok = false;             // generation 4 with cp.async staging is available (int16, M = 512, any D)
     int kernel_gen = 1;             // 3: warp-specialised kernel, 2: TMA + packed transforms, 1: first generation
     float2* d_tw = nullptr;
     float2* d_rot = nullptr;        // [C][ld] in-block NCO rotation table
@@ -261,7 +262,11 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         else mg_split = std::min(a.mg_end, t_row0 + t_rows);
         if (mg_split <= a.mg_begin) use_v2 = false;
     }
-    if (!use_v2) mg_split = a.mg_begin;
+    // what the tensor map cannot describe (D % 4 != 0, unaligned or partly resident buffers) goes to the same
+    // kernel with cp.async staging, which bounds-checks every frame itself and so takes the whole row range
+    const bool use_cp = !use_v2 && b->cp_ok;
+    if (use_cp) mg_split = a.mg_end;
+    else if (!use_v2) mg_split = a.mg_begin;
     for (const Group& g : b->groups) {
         ChannelizeParams p{};
         p.raw = a.d_raw;
@@ -281,13 +286,15 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         p.phase.seg0_n = a.seg_origin;
         p.phase.nseg = a.nseg;
         for (int i = 0; i < g.count; ++i) p.w[i] = b->w[g.first + i];
-        if (use_v2) {
+        if (use_v2 || use_cp) {
             p.mg_begin = a.mg_begin;
             p.mg_end = mg_split;
             p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
             p.gtab = b->d_gtab2 + g.g_off;
             p.out = b->d_bb + (size_t)g.first * stride;
-            if ((rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st, b->kernel_gen))) return rc;
+            if (use_v2) rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st, b->kernel_gen);
+            else rc = launch_channelize2_cp(p, g.count, b->n_sm, a.st);
+            if (rc) return rc;
             b->launches++;
             b->launches_v2++;
         }
@@ -636,20 +643,24 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     {
         const char* env = std::getenv("IQ2A_CHANNELIZER");
         const bool force_v1 = env && std::strcmp(env, "v1") == 0;
-        b->v2_ok = !force_v1 && M == 512 && cfg->codec == IQ2A_CODEC_S16 && D % 4 == 0 && channelize2_available();
-        b->kernel_gen = !b->v2_ok ? 1 : (env && std::strcmp(env, "v2") == 0) ? 2 : (env && std::strcmp(env, "v3") == 0) ? 3 : 4;
-        if (b->v2_ok && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
+        const bool bulk = !force_v1 && M == 512 && cfg->codec == IQ2A_CODEC_S16;
+        const char* stg = std::getenv("IQ2A_STAGING");               // "cp": cp.async staging even where TMA applies
+        b->v2_ok = bulk && D % 4 == 0 && channelize2_available() && !(stg && std::strcmp(stg, "cp") == 0);
+        const int want = (env && std::strcmp(env, "v2") == 0) ? 2 : (env && std::strcmp(env, "v3") == 0) ? 3 : 4;
+        b->cp_ok = bulk && want == 4;
+        b->kernel_gen = b->v2_ok ? want : (b->cp_ok ? 4 : 1);
+        if ((b->v2_ok || b->cp_ok) && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
     }
     for (const Group& g : b->groups)
         for (int i = 0; i < g.count; ++i) {
             const int c = g.first + i;
             rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
                                 b->d_gtab + g.g_off, g.count, i, 0, 1.0, b->stream);
-            if (!rc && b->v2_ok)
+            if (!rc && (b->v2_ok || b->cp_ok))
                 rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
                                     b->d_gtab2 + g.g_off, g.count, i, b->kernel_gen == 4 ? 2 : 1, 1.0 / 32768.0, b->stream);
             if (rc) { cudaFree(d_wtab); return fail(rc); }
-            b->launches += b->v2_ok ? 2 : 1;
+            b->launches += (b->v2_ok || b->cp_ok) ? 2 : 1;
         }
     b->tap_off = toff;
     if ((rc = dev_alloc(&b->d_rot, (size_t)C * b->ld)) || (rc = launch_build_rot(b->d_w, C, D, b->ld, b->d_rot, b->stream))) {

@@ -28,6 +28,8 @@ int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, i
 IQ2A_DECL2(1) IQ2A_DECL2(2) IQ2A_DECL2(3) IQ2A_DECL2(4) IQ2A_DECL2(5) IQ2A_DECL2(6)
 #define IQ2A_DECL2B(CG) int launch_channelize2b_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
 IQ2A_DECL2B(1) IQ2A_DECL2B(2) IQ2A_DECL2B(3) IQ2A_DECL2B(4) IQ2A_DECL2B(5) IQ2A_DECL2B(6)
+#define IQ2A_DECL2C(CG) int launch_channelize2c_##CG(const ChannelizeParams&, int, cudaStream_t);
+IQ2A_DECL2C(1) IQ2A_DECL2C(2) IQ2A_DECL2C(3) IQ2A_DECL2C(4) IQ2A_DECL2C(5) IQ2A_DECL2C(6)
 #define IQ2A_DECL3(CG) int launch_channelize3_##CG(const ChannelizeParams&, const CUtensorMap&, int64_t, int, cudaStream_t);
 IQ2A_DECL3(1) IQ2A_DECL3(2) IQ2A_DECL3(3) IQ2A_DECL3(4) IQ2A_DECL3(5) IQ2A_DECL3(6)
 
@@ -87,6 +89,17 @@ int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int6
     switch (cg) {
 #define IQ2A_CASE2(CG) case CG: return launch_channelize2_##CG(p, tmap, tmap_row0, n_sm, st);
         IQ2A_CASE2(1) IQ2A_CASE2(2) IQ2A_CASE2(3) IQ2A_CASE2(4) IQ2A_CASE2(5) IQ2A_CASE2(6)
+    }
+    set_error("unsupported channel group %d", cg);
+    return IQ2A_ERR_INVALID;
+}
+
+// Generation-4 kernel with cp.async staging: no tensor map, the kernel bounds-checks against p.raw_n0 / p.raw_len.
+int launch_channelize2_cp(const ChannelizeParams& p, int cg, int n_sm, cudaStream_t st) {
+    if (p.nblocks <= 0) return IQ2A_OK;
+    switch (cg) {
+#define IQ2A_CASE2C(CG) case CG: return launch_channelize2c_##CG(p, n_sm, st);
+        IQ2A_CASE2C(1) IQ2A_CASE2C(2) IQ2A_CASE2C(3) IQ2A_CASE2C(4) IQ2A_CASE2C(5) IQ2A_CASE2C(6)
     }
     set_error("unsupported channel group %d", cg);
     return IQ2A_ERR_INVALID;

@@ -13,6 +13,10 @@
 //  * int16 -> float conversion only (I2F); the 1/32768 scale is folded into the G table.
 //  * G is fetched two MAC steps ahead (the first two requests of a tile are issued before the barrier).
 //
+// STG = 1 replaces the TMA tensor copy by per-thread 4-byte cp.async copies (zero-filled out of range, completion
+// on the same mbarrier): any D, any 4-byte aligned buffer, rows that are only partly resident -- the cases the
+// tensor map cannot describe (row pitch D*4 B must be a multiple of 16 B for TMA).
+//
 // Shared memory: T[256][33] float4 (E.re,O.re,E.im,O.im) 135 168 B | PCM staging 4 x 16 512 B |
 // inverse twiddles 4 KB | pre-broadcast forward twiddles 4 KB | mbarrier.  Block b's PCM rows are
 // stored rotated by b rows so that the four blocks of a warp's 32 slots hit different banks.
@@ -67,6 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// 4-byte asynchronous copy, zero-filled when src_bytes == 0
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's earlier cp.async copies arrive on the mbarrier when they land (count pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -80,7 +92,7 @@ __host__ __device__ inline int slot_to_bin_v2(int j) {
     return (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
 }
 
-template <int CG, int BT>
+template <int CG, int BT, int STG = 0>
 __global__ void __launch_bounds__(Geo2<BT>::NT, 4 / BT)
 k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap, const int64_t tmap_row0) {
     using G2 = Geo2<BT>;
@@ -104,7 +116,7 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
         const float2 w = p.twid[2 * i];                       // W_256^i = W_512^{2i} = (cos, -sin)
         tw256b[i] = make_float4(w.x, w.x, w.y, w.y);
     }
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) mbar_init(bar, STG == 0 ? 1 : NT);
     __syncthreads();
 
     const int D = p.decim;
@@ -144,7 +156,30 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                     tma_load_2d(stage + b * kStageBytes + i * kBoxRows * 32, &tmap, t * P, rt + i * kBoxRows, bar);
             }
         };
-        if (tid == 0) issue(0);
+        // STG == 1: every thread copies one frame column of 32-row sweeps; same staging layout as the TMA boxes
+        auto issue_cp = [&](int t) {
+            const int col = tid & 7, jr = tid >> 3;
+            const bool col_ok = t * P + col < D;
+            const uint32_t* raw = reinterpret_cast<const uint32_t*>(p.raw);
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                const int64_t row0 = p.mg_begin + (int64_t)(blk0 + b) * p.ld - p.vd;
+                int64_t f = (row0 - b + jr) * (int64_t)D + t * P + col - p.raw_n0;       // frame offset into p.raw
+                uint32_t dst = smem_u32(stage + b * kStageBytes + jr * 32 + col * 4);
+                for (int j = jr; j < kStageRows; j += NT / 8) {
+                    const bool ok = col_ok && f >= 0 && f < p.raw_len;
+                    cp_async4(dst, raw + (ok ? f : 0), ok ? 4 : 0);
+                    f += (int64_t)(NT / 8) * D;
+                    dst += (NT / 8) * 32;
+                }
+            }
+            cp_async_arrive(bar);
+        };
+        if constexpr (STG == 0) {
+            if (tid == 0) issue(0);
+        } else {
+            issue_cp(0);
+        }
 
         for (int t = 0; t < ntiles; ++t) {
             mbar_wait(bar, parity);
@@ -189,7 +224,11 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                 });
             }
             __syncthreads();
-            if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+            if constexpr (STG == 0) {
+                if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+            } else {
+                if (t + 1 < ntiles) issue_cp(t + 1);
+            }
             // ------------- pass 2: 16-point DIF over m2, in place ----------------------------------------
             {
                 const int k1 = rg;
@@ -311,10 +350,10 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
     }
 }
 
-template <int CG, int BT>
+template <int CG, int BT, int STG = 0>
 static int launch_channelize2_cg(const ChannelizeParams& p, const CUtensorMap& tmap, int64_t tmap_row0, int n_sm,
                                  cudaStream_t st) {
-    auto kern = k_channelize2<CG, BT>;
+    auto kern = k_channelize2<CG, BT, STG>;
     static bool configured = false;
     if (!configured) {
         IQ2A_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo2<BT>::smem));

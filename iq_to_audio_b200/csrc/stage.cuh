@@ -36,6 +36,7 @@ int launch_build_rot(const double* d_w, int nchan, int D, int ld, float2* d_rot,
 int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, int n_sm, cudaStream_t st);
 int channelize_max_group(int m_fft);
 bool channelize2_available();
+int launch_channelize2_cp(const ChannelizeParams& p, int cg, int n_sm, cudaStream_t st);
 int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
                        int n_sm, cudaStream_t st, int generation);
 
