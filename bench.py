@@ -37,6 +37,7 @@ SECONDS = 60.0
 OFFSETS = [-3.2e6, -1.1e6, 0.4e6, 2.3e6, 4.1e6]
 BW = 12_500.0
 DEEMPH_US = 300.0
+SM_RESERVE = 8            # multi-GPU runs: SMs left to the NCCL audio gather (of 148)
 REQ_CHUNK = 1_048_576
 METRIC = "input complex Msamples/s"
 UNIT = "Msamples/s"
@@ -206,6 +207,8 @@ def main() -> None:
     ap.add_argument("--seconds", type=float, default=SECONDS, help="capture length per GPU (default 60 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="multi-GPU: gather the audio with NCCL instead of the peer-memory pull")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,6 +260,9 @@ def main() -> None:
     if world > 1:
         # keep stdout to the single JSON line: NCCL's version/info banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the audio gather runs on at most SM_RESERVE channels: that many SMs are kept free of the persistent
+        # channel-bank kernel below, so the gather of step k really overlaps the compute of step k+1
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(SM_RESERVE))
         dist.init_process_group("nccl", device_id=dev)
 
     n_seg = int(round(FS * args.seconds))
@@ -268,15 +274,40 @@ def main() -> None:
     warm_rows, seg_begin, seg_end, first = seg.warmup_rows, seg.begin, seg.end, seg.first_frame
     capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
-    # two audio buffers: the NCCL gather of step k (NVLink, rank 0's ingress) runs while step k+1 computes
-    audio_bufs = [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
-    gathered = [[torch.empty_like(audio_bufs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else None
+    # two audio slots: the gather of step k (NVLink, rank 0's ingress) runs while step k+1 computes.  Preferred:
+    # peer-memory pull by copy engines (sharding.PeerGather); fallback: NCCL gather.
+    comp = torch.cuda.Stream(device=dev)
+    peer = None
+    if world > 1 and not args.nccl_gather:
+        try:
+            peer = sharding.PeerGather((bank.n_channels, rows), torch.float32, dev)
+        except Exception as exc:                      # symmetric memory unavailable on this box / build
+            print(f"[bench] peer-memory gather unavailable ({exc!r}); using the NCCL gather", file=sys.stderr)
+            peer = None
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+    if world > 1 and peer is None:
+        bank.set_sm_reserve(SM_RESERVE)              # room for the NCCL gather's CTAs next to the persistent kernel
+    audio_bufs = None if peer is not None else \
+        [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    gathered = [[torch.empty_like(audio_bufs[0]) for _ in range(world)] for _ in range(2)] \
+        if (world > 1 and rank == 0 and peer is None) else None
     pending = [None, None]
     step_no = [0]
 
     def resident_step():
-        k = step_no[0] % len(audio_bufs)
+        kk = step_no[0]
         step_no[0] += 1
+        if peer is not None:
+            audio = peer.slot(kk)
+            bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
+                                        warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows,
+                                        stream=comp.cuda_stream)
+            peer.publish(kk, comp)
+            return
+        k = kk % len(audio_bufs)
         if pending[k] is not None:          # the gather that last read this buffer must be done
             pending[k].wait()
             pending[k] = None
@@ -287,6 +318,9 @@ def main() -> None:
             pending[k] = dist.gather(audio, gathered[k] if gathered else None, dst=0, async_op=True)
 
     def drain():
+        if peer is not None:
+            comp.synchronize()
+            peer.drain()
         for k in range(len(pending)):
             if pending[k] is not None:
                 pending[k].wait()
@@ -302,6 +336,19 @@ def main() -> None:
     for _ in range(warmup):
         resident_step()
     sync_all()
+    # what arrived on rank 0 is what the ranks produced: compare per-rank checksums of the last warm-up step
+    gather_ok = None
+    if world > 1:
+        last = step_no[0] - 1
+        mine = (peer.slot(last) if peer is not None else audio_bufs[last % 2]).double().abs().sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            got = peer.result(last) if peer is not None else gathered[last % 2]
+            gather_ok = all(abs(float(g.double().abs().sum()) - float(sums[r])) <= 1e-9 * max(1.0, float(sums[r]))
+                            for r, g in enumerate(got))
+            if not gather_ok:
+                raise SystemExit("gathered audio does not match what the ranks produced")
     bank.set_timing(True)
     launches0 = bank.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -413,7 +460,9 @@ def main() -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
         "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
-                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}",
+                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_gather": (0 if peer is not None else SM_RESERVE) if world > 1 else 0,
+                   "gather": "none" if world == 1 else ("peer-memory pull over NVLink (copy engines)" if peer is not None else "nccl gather"),
+                   "gather_verified": gather_ok,
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

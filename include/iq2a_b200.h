@@ -171,6 +171,9 @@ int iq2a_bank_launch_count(const iq2a_bank* bank, int64_t* launches);
 int iq2a_bank_set_timing(iq2a_bank* bank, int32_t enable);
 int iq2a_bank_get_timing(iq2a_bank* bank, double* channelize_ms, double* head_ms, double* tail_ms,
                          int64_t* calls);
+/* Multi-GPU hosts: keep `n_sm` multiprocessors free of the persistent channel-bank kernel so that a concurrent
+ * collective (the NCCL gather of the previous segment's audio) can be scheduled while it runs.  0 = use all. */
+int iq2a_bank_set_sm_reserve(iq2a_bank* bank, int32_t n_sm);
 /* debug / tests: copy the bank's G table (complex64 [C][D][M], slot order) to host */
 int iq2a_bank_copy_gtable(const iq2a_bank* bank, float* host_out, int64_t n_complex);
 

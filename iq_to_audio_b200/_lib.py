@@ -28,7 +28,7 @@ SYMBOLS = (
     "iq2a_bank_get_state", "iq2a_bank_set_state", "iq2a_bank_process_chunk",
     "iq2a_bank_submit_chunk", "iq2a_bank_collect_chunk",
     "iq2a_bank_process_resident", "iq2a_bank_process_resident_async", "iq2a_bank_launch_count",
-    "iq2a_bank_copy_gtable", "iq2a_bank_set_timing", "iq2a_bank_get_timing",
+    "iq2a_bank_copy_gtable", "iq2a_bank_set_timing", "iq2a_bank_get_timing", "iq2a_bank_set_sm_reserve",
     "iq2a_unpack_mix", "iq2a_fir", "iq2a_decimate", "iq2a_demod", "iq2a_scan",
     "iq2a_resampler_create", "iq2a_resampler_destroy", "iq2a_resampler_process", "iq2a_resampler_flush",
     "iq2a_resampler_max_outputs",
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     lib.iq2a_bank_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.iq2a_bank_copy_gtable.argtypes = [vp, fp, i64]
     lib.iq2a_bank_set_timing.argtypes = [vp, i32]
+    lib.iq2a_bank_set_sm_reserve.argtypes = [vp, i32]
     lib.iq2a_bank_get_timing.argtypes = [vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(i64)]
     lib.iq2a_unpack_mix.argtypes = [vp, i64, i32, i32, f64, f64, fp, i32]
     lib.iq2a_fir.argtypes = [fp, i64, fp, C.POINTER(f64), i32, fp, i32]

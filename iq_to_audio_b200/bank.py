@@ -132,6 +132,10 @@ class ChannelBank:
         _lib.check(self._lib.iq2a_bank_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def set_sm_reserve(self, n_sm: int) -> None:
+        """Keep `n_sm` SMs free of the persistent channel-bank kernel (room for a concurrent NCCL gather)."""
+        _lib.check(self._lib.iq2a_bank_set_sm_reserve(self._h, int(n_sm)))
+
     def set_timing(self, enable: bool = True) -> None:
         _lib.check(self._lib.iq2a_bank_set_timing(self._h, 1 if enable else 0))
 

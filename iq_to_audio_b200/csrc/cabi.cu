@@ -102,7 +102,7 @@ using namespace iq2a;
 
 struct iq2a_bank {
     iq2a_bank_config cfg{};
-    int C = 0, D = 1, M = 0, R1 = 32, vd = 0, ld = 0, n_sm = 148;
+    int C = 0, D = 1, M = 0, R1 = 32, vd = 0, ld = 0, n_sm = 148, n_sm_total = 148;
     bool any_agc = false;
     int64_t tail_fused_w = 0;   // > 0: the single-pass tail applies (tail.cuh)
     std::vector<std::vector<double>> taps;
@@ -544,7 +544,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", cfg->device); return fail(IQ2A_ERR_CUDA); }
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(IQ2A_ERR_CUDA); }
-    b->n_sm = prop.multiProcessorCount;
+    b->n_sm = b->n_sm_total = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(IQ2A_ERR_CUDA); }
 
     const int C = b->C;
@@ -724,6 +724,13 @@ int iq2a_bank_set_state(iq2a_bank* b, const iq2a_channel_state* states) {
 int iq2a_bank_launch_count(const iq2a_bank* b, int64_t* launches) {
     if (!b || !launches) { set_error("null argument"); return IQ2A_ERR_INVALID; }
     *launches = b->launches;
+    return IQ2A_OK;
+}
+
+int iq2a_bank_set_sm_reserve(iq2a_bank* b, int32_t n_sm) {
+    if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
+    if (n_sm < 0 || n_sm >= b->n_sm_total) { set_error("sm reserve %d out of range [0, %d)", n_sm, b->n_sm_total); return IQ2A_ERR_INVALID; }
+    b->n_sm = b->n_sm_total - n_sm;
     return IQ2A_OK;
 }
 

@@ -36,6 +36,7 @@ import numpy as np
 
 from . import _lib
 from .bank import ChannelBank, Target
+from .input_formats import probe_wav, resolve_input_format
 from .processing import channel_decimation, choose_mix_sign, design_channel_filter, tune_chunk_size
 
 LOG = logging.getLogger(__name__)
@@ -127,56 +128,22 @@ class InputFormat:
         return _FRAME_BYTES[self.codec]
 
 
-def _scan_wav(path: Path) -> InputFormat:
-    """Walk the RIFF chunks up to 'data'.  The data chunk's declared length is ignored and the
-    payload is read to end of file -- what `-ignore_length 1` does for > 4 GiB SDR++ captures
-    (ref: processing.py:149-150)."""
-    with path.open("rb") as fh:
-        head = fh.read(12)
-        if len(head) < 12 or head[:4] not in (b"RIFF", b"RF64") or head[8:12] != b"WAVE":
-            raise ValueError(f"{path} is not a RIFF/WAVE file")
-        codec, rate, channels = None, None, None
-        while True:
-            hdr = fh.read(8)
-            if len(hdr) < 8:
-                raise ValueError(f"{path}: no data chunk")
-            tag, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
-            if tag == b"fmt ":
-                body = fh.read(size + (size & 1))
-                fmt, channels, rate, _, _, bits = struct.unpack("<HHIIHH", body[:16])
-                if fmt == 0xFFFE and len(body) >= 26:
-                    fmt = struct.unpack("<H", body[24:26])[0]
-                codec = {(1, 8): "pcm_u8", (1, 16): "pcm_s16le", (3, 32): "pcm_f32le"}.get((fmt, bits))
-                if codec is None:
-                    raise ValueError(f"{path}: unsupported WAV encoding (format {fmt}, {bits} bits)")
-            elif tag == b"data":
-                if codec is None:
-                    raise ValueError(f"{path}: data chunk before fmt chunk")
-                if channels != 2:
-                    raise ValueError(f"{path}: expected a 2-channel (I/Q) capture, found {channels} channels")
-                return InputFormat("wav", codec, float(rate), fh.tell())
-            else:
-                fh.seek(size + (size & 1), os.SEEK_CUR)
-
-
 def resolve_input(path: Path, requested: str | None, container_hint: str | None,
                   sample_rate: float | None) -> InputFormat:
-    container, codec = container_hint, None
-    if requested:
-        key = requested.lower()
-        if key not in _CODEC_BY_FORMAT:
-            raise ValueError(f"Unsupported input format '{requested}'")
-        c, codec = _CODEC_BY_FORMAT[key]
-        container = c or container
-    suffix = path.suffix.lower()
-    if container is None:
-        container = "raw" if suffix in _RAW_SUFFIX else "wav"
-    if container == "raw":
-        return InputFormat("raw", codec or _RAW_SUFFIX.get(suffix, "pcm_s16le"), sample_rate, 0)
-    fmt = _scan_wav(path)
-    if codec:
-        fmt.codec = codec
-    return fmt
+    """Effective encoding (input_formats.resolve_input_format: override or detection, same errors as the
+    reference) plus what the raw-frame reader needs from a WAV header: payload offset and sample rate.  The data
+    chunk's declared length is ignored and the payload is read to end of file -- what `-ignore_length 1` does for
+    > 4 GiB SDR++ captures (ref: processing.py:149-150)."""
+    spec, _source = resolve_input_format(Path(path), requested=requested, container_hint=container_hint)
+    if spec.container == "raw":
+        return InputFormat("raw", spec.codec, sample_rate, 0)
+    try:
+        header = probe_wav(Path(path))
+    except RuntimeError as exc:
+        raise ValueError(str(exc)) from exc
+    if header.channels != 2:
+        raise ValueError(f"{path}: expected a 2-channel (I/Q) capture, found {header.channels} channels")
+    return InputFormat("wav", spec.codec, float(header.sample_rate), header.data_offset)
 
 
 class IQReader:

@@ -87,3 +87,78 @@ def reduce_peak(local_peaks, dst: int = 0):
     import torch.distributed as dist
     dist.reduce(local_peaks, dst=dst, op=dist.ReduceOp.MAX)
     return local_peaks
+
+
+class PeerGather:
+    """Audio gather over NVLink peer memory, for pipelined steps on the GPUs of one box.
+
+    Every rank writes its rows straight into a slot of a symmetric (peer-mapped) buffer; rank `dst` pulls the
+    slots of the other ranks with device-to-device copies on a side stream -- copy engines over NVSwitch, no SMs,
+    so the pull of step k runs under the persistent channel-bank kernel of step k+1 (an NCCL gather needs SMs that
+    the kernel occupies and ends up serialised behind it).  A signal-pad barrier per step on the compute stream
+    orders producers and the consumer:
+
+        compute(k) -> [dst: wait until pull(k-1) finished] -> barrier(k) -> compute(k+1) ...
+                                                                 \\-> dst side stream: pull(k)
+
+    With two slots, slot k%2 is rewritten by compute(k+2), which every rank enqueues behind barrier(k+1), and dst
+    enters barrier(k+1) only after pull(k) has finished.  `torch.distributed._symmetric_memory` provides the
+    allocation, the peer views and the barrier; NCCL is not involved in the data path.
+    """
+
+    def __init__(self, shape, dtype, device, *, dst: int = 0, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch = torch
+        self.rank, self.world, self.dst, self.depth = dist.get_rank(), dist.get_world_size(), dst, depth
+        self.shape, self.dtype = tuple(shape), dtype
+        self.numel = 1
+        for v in self.shape:
+            self.numel *= int(v)
+        self.buf = symm.empty((depth, *self.shape), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.pull_stream = torch.cuda.Stream(device=device) if self.rank == dst else None
+        self.pulled = [None] * depth            # dst: event "pull of this slot finished"
+        self.out = None
+        if self.rank == dst:
+            self.out = [[torch.empty(self.shape, dtype=dtype, device=device) for _ in range(self.world)]
+                        for _ in range(depth)]
+            self.peers = [[self.hdl.get_buffer(r, self.shape, dtype, s * self.numel) for r in range(self.world)]
+                          for s in range(depth)]
+
+    def slot(self, k: int):
+        return self.buf[k % self.depth]
+
+    def publish(self, k: int, stream) -> None:
+        """Call once the kernels producing slot k have been enqueued on `stream` (the compute stream)."""
+        torch = self.torch
+        s = k % self.depth
+        with torch.cuda.stream(stream):
+            if self.rank == self.dst:
+                prev = self.pulled[(k + 1) % self.depth]
+                if prev is not None:
+                    stream.wait_event(prev)
+            self.hdl.barrier(channel=0)
+            if self.rank == self.dst:
+                ready = torch.cuda.Event()
+                ready.record(stream)
+        if self.rank == self.dst:
+            self.pull_stream.wait_event(ready)
+            with torch.cuda.stream(self.pull_stream):
+                for r in range(self.world):
+                    if r != self.dst:
+                        self.out[s][r].copy_(self.peers[s][r], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.pull_stream)
+            self.pulled[s] = done
+
+    def result(self, k: int):
+        """dst only: list of per-rank tensors of step k (own slot included), valid after `drain()`."""
+        s = k % self.depth
+        self.out[s][self.dst] = self.buf[s]
+        return self.out[s]
+
+    def drain(self) -> None:
+        if self.pull_stream is not None:
+            self.pull_stream.synchronize()
