@@ -37,7 +37,7 @@ SECONDS = 60.0
 OFFSETS = [-3.2e6, -1.1e6, 0.4e6, 2.3e6, 4.1e6]
 BW = 12_500.0
 DEEMPH_US = 300.0
-SM_RESERVE = 8            # multi-GPU runs: SMs left to the NCCL audio gather (of 148)
+SM_RESERVE = 0            # multi-GPU runs: SMs kept free of the persistent kernel for NCCL (--sm-reserve; measured: no gain)
 REQ_CHUNK = 1_048_576
 METRIC = "input complex Msamples/s"
 UNIT = "Msamples/s"
@@ -207,8 +207,11 @@ def main() -> None:
     ap.add_argument("--seconds", type=float, default=SECONDS, help="capture length per GPU (default 60 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--nccl-gather", action="store_true",
-                    help="multi-GPU: gather the audio with NCCL instead of the peer-memory pull")
+    ap.add_argument("--peer-gather", action="store_true",
+                    help="multi-GPU: push the audio into rank 0's memory with copy engines (sharding.PeerGather) "
+                         "instead of the NCCL gather")
+    ap.add_argument("--sm-reserve", type=int, default=int(os.environ.get("IQ2A_BENCH_SM_RESERVE", SM_RESERVE)),
+                    help="multi-GPU: SMs kept free of the persistent kernel for the NCCL gather (= NCCL channels)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -262,7 +265,8 @@ def main() -> None:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the audio gather runs on at most SM_RESERVE channels: that many SMs are kept free of the persistent
         # channel-bank kernel below, so the gather of step k really overlaps the compute of step k+1
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(SM_RESERVE))
+        if args.sm_reserve > 0:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.sm_reserve))
         dist.init_process_group("nccl", device_id=dev)
 
     n_seg = int(round(FS * args.seconds))
@@ -275,10 +279,10 @@ def main() -> None:
     capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
     # two audio slots: the gather of step k (NVLink, rank 0's ingress) runs while step k+1 computes.  Preferred:
-    # peer-memory pull by copy engines (sharding.PeerGather); fallback: NCCL gather.
+    # peer-memory push by copy engines (sharding.PeerGather); fallback: NCCL gather.
     comp = torch.cuda.Stream(device=dev)
     peer = None
-    if world > 1 and not args.nccl_gather:
+    if world > 1 and args.peer_gather:
         try:
             peer = sharding.PeerGather((bank.n_channels, rows), torch.float32, dev)
         except Exception as exc:                      # symmetric memory unavailable on this box / build
@@ -289,42 +293,48 @@ def main() -> None:
         if int(ok.item()) == 0:
             peer = None
     if world > 1 and peer is None:
-        bank.set_sm_reserve(SM_RESERVE)              # room for the NCCL gather's CTAs next to the persistent kernel
+        bank.set_sm_reserve(args.sm_reserve)         # room for the NCCL gather's CTAs next to the persistent kernel
     audio_bufs = None if peer is not None else \
         [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
-    gathered = [[torch.empty_like(audio_bufs[0]) for _ in range(world)] for _ in range(2)] \
-        if (world > 1 and rank == 0 and peer is None) else None
-    pending = [None, None]
+    # default: per-target writers (sharding.WriterExchange): target c is assembled on rank c % N, balanced exchange
+    xchg = sharding.WriterExchange(bank.n_channels, rows, torch.float32, dev) if (world > 1 and peer is None) else None
     step_no = [0]
+    host_publish = []
 
     def resident_step():
         kk = step_no[0]
         step_no[0] += 1
         if peer is not None:
             audio = peer.slot(kk)
+            peer.before_compute(kk, comp)
             bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
                                         warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows,
                                         stream=comp.cuda_stream)
+            t_h = time.perf_counter()
             peer.publish(kk, comp)
+            host_publish.append(time.perf_counter() - t_h)
             return
         k = kk % len(audio_bufs)
-        if pending[k] is not None:          # the gather that last read this buffer must be done
-            pending[k].wait()
-            pending[k] = None
         audio = audio_bufs[k]
-        bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
-                              warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
-        if world > 1:
-            pending[k] = dist.gather(audio, gathered[k] if gathered else None, dst=0, async_op=True)
+        if world == 1:
+            bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
+                                  warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
+            return
+        # multi-GPU: everything on one stream, the host runs ahead.  The exchange follows the kernels of its step
+        # (measured: NCCL's CTAs cannot be scheduled next to the persistent channel-bank kernel, and when they can --
+        # reserved SMs, fewer channels -- the two slow each other down by more than the overlap gains), with every
+        # SM and NVLink channel to itself it takes 0.25-0.4 ms of a 2.5 ms step.
+        with torch.cuda.stream(comp):
+            bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
+                                        warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows,
+                                        stream=comp.cuda_stream)
+            for wk in xchg.exchange(k, audio):
+                wk.wait()                    # orders `comp` behind the collective; does not block the host
 
     def drain():
         if peer is not None:
-            comp.synchronize()
-            peer.drain()
-        for k in range(len(pending)):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
+            peer.flush(step_no[0] - 1, comp)
+        comp.synchronize()
 
     def sync_all():
         drain()
@@ -336,19 +346,26 @@ def main() -> None:
     for _ in range(warmup):
         resident_step()
     sync_all()
-    # what arrived on rank 0 is what the ranks produced: compare per-rank checksums of the last warm-up step
+    # what arrived at the writers is what the ranks produced: per-(rank, target) checksums of the last warm-up step
     gather_ok = None
     if world > 1:
         last = step_no[0] - 1
-        mine = (peer.slot(last) if peer is not None else audio_bufs[last % 2]).double().abs().sum().reshape(1)
+        src = peer.slot(last) if peer is not None else audio_bufs[last % 2]
+        mine = src.double().abs().sum(dim=1)                         # [C]
         sums = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(sums, mine)
-        if rank == 0:
-            got = peer.result(last) if peer is not None else gathered[last % 2]
-            gather_ok = all(abs(float(g.double().abs().sum()) - float(sums[r])) <= 1e-9 * max(1.0, float(sums[r]))
-                            for r, g in enumerate(got))
-            if not gather_ok:
-                raise SystemExit("gathered audio does not match what the ranks produced")
+        sums = torch.stack(sums)                                     # [world, C]
+        if peer is not None:
+            ok = rank != 0 or all(abs(float(g.double().abs().sum()) - float(sums[r].sum())) <= 1e-9 * max(1.0, float(sums[r].sum()))
+                                  for r, g in enumerate(peer.result(last)))
+        else:
+            ok = all(float((blk.double().abs().sum(dim=1) - sums[:, c]).abs().max()) <= 1e-9 * max(1.0, float(sums[:, c].max()))
+                     for c, blk in xchg.result(last % 2).items())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(int(flag.item()))
+        if not gather_ok:
+            raise SystemExit("exchanged audio does not match what the ranks produced")
     bank.set_timing(True)
     launches0 = bank.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,6 +379,20 @@ def main() -> None:
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
+    if world > 1 and xchg is not None and os.environ.get("IQ2A_BENCH_DEBUG"):
+        # the exchange alone, nothing else running: what has to hide under a step
+        sync_all()
+        tx = []
+        for _ in range(3):
+            dist.barrier(); torch.cuda.synchronize()
+            t_a = time.perf_counter()
+            for wk in xchg.exchange(0, audio_bufs[0]):
+                wk.wait()
+            torch.cuda.synchronize()
+            tx.append((time.perf_counter() - t_a) * 1e3)
+        print(f"[bench] rank {rank}: exchange alone ms {[round(v, 3) for v in tx]}; step wall {wall * 1e3 / steps:.3f}", file=sys.stderr)
+    if host_publish and os.environ.get("IQ2A_BENCH_DEBUG"):
+        print(f"[bench] rank {rank}: host ms in publish(): {[round(v * 1e3, 3) for v in host_publish[-steps:]]} wall {wall * 1e3:.3f} dev {dev_ms:.3f}", file=sys.stderr)
     # the bank launches on its own stream: the wall clock bracketed by synchronize is the step time;
     # the CUDA events on torch's stream only bound the gather
     step_ms = max(dev_ms, wall * 1e3) / steps
@@ -460,8 +491,8 @@ def main() -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
         "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
-                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_gather": (0 if peer is not None else SM_RESERVE) if world > 1 else 0,
-                   "gather": "none" if world == 1 else ("peer-memory pull over NVLink (copy engines)" if peer is not None else "nccl gather"),
+                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_gather": (0 if peer is not None else args.sm_reserve) if world > 1 else 0,
+                   "gather": "none" if world == 1 else ("peer-memory push to rank 0 (copy engines)" if peer is not None else "per-target writers: all_to_all_single over NCCL, target c on rank c % N"),
                    "gather_verified": gather_ok,
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,

@@ -89,76 +89,146 @@ def reduce_peak(local_peaks, dst: int = 0):
     return local_peaks
 
 
+class WriterExchange:
+    """Per-target writers: the audio of target c from every time shard is assembled on rank c % world.
+
+    One output file per target means one writer per target; spreading the writers over the ranks turns the
+    many-to-one gather (rank 0 would take in (world-1)/world of ALL audio, every step) into a balanced exchange in
+    which a writer receives only its own targets.  Channels are dealt round-robin, so the rows a rank sends in
+    round j -- targets j*world .. j*world+world-1, one per destination in rank order -- are contiguous in the
+    [C, rows] audio layout and go out as one `all_to_all_single` with split sizes (NCCL on GPUs, gloo in the CPU
+    tests); no packing kernel, no copy.
+    """
+
+    def __init__(self, n_channels: int, rows: int, dtype, device, *, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.C, self.rows = int(n_channels), int(rows)
+        self.rounds = (self.C + self.world - 1) // self.world
+        self.owned = [c for c in range(self.C) if c % self.world == self.rank]
+        self.empty = torch.empty(0, dtype=dtype, device=device)
+        # recv[slot][j]: [world, rows] -- target j*world + rank as produced by shard 0 .. world-1
+        self.recv = [[torch.empty((self.world, self.rows), dtype=dtype, device=device) for _ in self.owned]
+                     for _ in range(depth)]
+
+    def exchange(self, slot: int, audio, *, async_op: bool = True):
+        """audio: [C, rows] of this rank's shard.  Returns the list of work handles (one per round)."""
+        works = []
+        w = self.world
+        for j in range(self.rounds):
+            lo, hi = j * w, min(self.C, (j + 1) * w)
+            send = audio[lo:hi].reshape(-1)
+            in_split = [self.rows if lo + r < self.C else 0 for r in range(w)]
+            mine = lo + self.rank < self.C
+            out = self.recv[slot][j].reshape(-1) if mine else self.empty
+            out_split = [self.rows if mine else 0] * w
+            works.append(self.dist.all_to_all_single(out, send, out_split, in_split, async_op=async_op))
+        return works
+
+    def result(self, slot: int) -> dict:
+        """{target: [world, rows]} for the targets this rank writes (rows of shard s in row s)."""
+        return {c: self.recv[slot][j] for j, c in enumerate(self.owned)}
+
+
 class PeerGather:
     """Audio gather over NVLink peer memory, for pipelined steps on the GPUs of one box.
 
-    Every rank writes its rows straight into a slot of a symmetric (peer-mapped) buffer; rank `dst` pulls the
-    slots of the other ranks with device-to-device copies on a side stream -- copy engines over NVSwitch, no SMs,
-    so the pull of step k runs under the persistent channel-bank kernel of step k+1 (an NCCL gather needs SMs that
-    the kernel occupies and ends up serialised behind it).  A signal-pad barrier per step on the compute stream
-    orders producers and the consumer:
+    Rank `dst` owns a receive area that every rank can address (symmetric memory).  After the kernels of step k,
+    each other rank pushes its rows into its place in that area with one device-to-device copy on a side stream:
+    world-1 copy engines write over NVSwitch in parallel (measured 740 GB/s per engine, unaffected by SM load,
+    tools/peer_copy_probe.py), no SMs are used, so the transfer of step k runs under the persistent channel-bank
+    kernel of step k+1.  (An NCCL gather needs SMs that the kernel occupies and ends up serialised behind it.)
 
-        compute(k) -> [dst: wait until pull(k-1) finished] -> barrier(k) -> compute(k+1) ...
-                                                                 \\-> dst side stream: pull(k)
+        compute stream :  compute(k) -> wait push(k-1) -> [dst: wait consume(k-2)] -> barrier(k) -> compute(k+1)
+        side stream    :  wait compute(k) -> push(k)            dst: wait barrier(k) -> consume(k-1)
 
-    With two slots, slot k%2 is rewritten by compute(k+2), which every rank enqueues behind barrier(k+1), and dst
-    enters barrier(k+1) only after pull(k) has finished.  `torch.distributed._symmetric_memory` provides the
-    allocation, the peer views and the barrier; NCCL is not involved in the data path.
+    The signal-pad barrier sits on the compute stream, between two steps, where SMs are free (next to the
+    persistent kernel it could not be scheduled).  Once barrier(k) has passed on `dst`, every push(k-1) has landed.
+    Three slots make reuse strict: push(k+3) overwrites slot k%3 after the sender's barrier(k+2), which `dst` enters
+    only after consume(k).  `torch.distributed._symmetric_memory` provides the allocation, the peer views and the
+    barrier; NCCL is not in the data path.
     """
 
-    def __init__(self, shape, dtype, device, *, dst: int = 0, depth: int = 2):
+    DEPTH = 3
+
+    def __init__(self, shape, dtype, device, *, dst: int = 0):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
-        self.torch = torch
-        self.rank, self.world, self.dst, self.depth = dist.get_rank(), dist.get_world_size(), dst, depth
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
         self.shape, self.dtype = tuple(shape), dtype
-        self.numel = 1
+        numel = 1
         for v in self.shape:
-            self.numel *= int(v)
-        self.buf = symm.empty((depth, *self.shape), dtype=dtype, device=device)
-        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
-        self.pull_stream = torch.cuda.Stream(device=device) if self.rank == dst else None
-        self.pulled = [None] * depth            # dst: event "pull of this slot finished"
-        self.out = None
-        if self.rank == dst:
-            self.out = [[torch.empty(self.shape, dtype=dtype, device=device) for _ in range(self.world)]
-                        for _ in range(depth)]
-            self.peers = [[self.hdl.get_buffer(r, self.shape, dtype, s * self.numel) for r in range(self.world)]
-                          for s in range(depth)]
+            numel *= int(v)
+        depth = self.DEPTH
+        self.local = [torch.empty(self.shape, dtype=dtype, device=device) for _ in range(depth)]
+        self.recv = symm.empty((depth, self.world, *self.shape), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.recv, dist.group.WORLD)
+        self.side = torch.cuda.Stream(device=device)
+        self.pushed = {}                        # step -> event: push has left the local slot and landed on dst
+        self.consumed = {}                      # dst: step -> event: consumer work finished
+        self.consumer = None                    # dst: callable(step, tensors) run on the side stream
+        self.mine_on_dst = [self.hdl.get_buffer(dst, self.shape, dtype, (s * self.world + self.rank) * numel)
+                            for s in range(depth)]
 
     def slot(self, k: int):
-        return self.buf[k % self.depth]
+        return self.local[k % self.DEPTH]
+
+    def before_compute(self, k: int, stream) -> None:
+        """Order the kernels that will overwrite slot k behind the push that last read it."""
+        ev = self.pushed.pop(k - self.DEPTH, None)
+        if ev is not None:
+            stream.wait_event(ev)
 
     def publish(self, k: int, stream) -> None:
         """Call once the kernels producing slot k have been enqueued on `stream` (the compute stream)."""
         torch = self.torch
-        s = k % self.depth
-        with torch.cuda.stream(stream):
-            if self.rank == self.dst:
-                prev = self.pulled[(k + 1) % self.depth]
-                if prev is not None:
-                    stream.wait_event(prev)
-            self.hdl.barrier(channel=0)
-            if self.rank == self.dst:
-                ready = torch.cuda.Event()
-                ready.record(stream)
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            if self.rank != self.dst:
+                self.mine_on_dst[k % self.DEPTH].copy_(self.local[k % self.DEPTH], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.pushed[k] = done
+        prev = self.pushed.get(k - 1)
+        if prev is not None:
+            stream.wait_event(prev)
         if self.rank == self.dst:
-            self.pull_stream.wait_event(ready)
-            with torch.cuda.stream(self.pull_stream):
-                for r in range(self.world):
-                    if r != self.dst:
-                        self.out[s][r].copy_(self.peers[s][r], non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(self.pull_stream)
-            self.pulled[s] = done
+            old = self.consumed.pop(k - 2, None)
+            if old is not None:
+                stream.wait_event(old)
+        with torch.cuda.stream(stream):
+            self.hdl.barrier(channel=0)
+        if self.rank == self.dst and k >= 1:
+            landed = torch.cuda.Event()
+            landed.record(stream)
+            self._consume(k - 1, landed)
+
+    def _consume(self, k: int, after) -> None:
+        torch = self.torch
+        self.side.wait_event(after)
+        with torch.cuda.stream(self.side):
+            if self.consumer is not None:
+                self.consumer(k, self.result(k))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.consumed[k] = ev
 
     def result(self, k: int):
-        """dst only: list of per-rank tensors of step k (own slot included), valid after `drain()`."""
-        s = k % self.depth
-        self.out[s][self.dst] = self.buf[s]
-        return self.out[s]
+        """dst only: per-rank tensors of step k (valid for the consumer, or after `flush`)."""
+        s = k % self.DEPTH
+        return [self.local[s] if r == self.dst else self.recv[s, r] for r in range(self.world)]
 
-    def drain(self) -> None:
-        if self.pull_stream is not None:
-            self.pull_stream.synchronize()
+    def flush(self, last_step: int, stream) -> None:
+        """After the last publish: wait until every push has landed and the consumer has seen the last step."""
+        stream.synchronize()
+        self.side.synchronize()
+        self.dist.barrier()
+        if self.rank == self.dst and last_step >= 0 and last_step not in self.consumed:
+            self._consume(last_step, self.torch.cuda.Event())
+            self.side.synchronize()

@@ -97,3 +97,44 @@ def test_two_rank_time_sharding_reproduces_single_stream():
     assert audio.size == g["audio"].size                      # exact row partition, in order
     assert np.abs(audio - g["audio"]).max() <= 1e-6           # halo + 600-row warm-up: < 1e-8 expected
     assert abs(ret["peak"] - float(g["peak"])) <= 1e-6
+
+
+def _xchg_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c_total, rows = 5, 37
+        x = sharding.WriterExchange(c_total, rows, torch.float32, torch.device("cpu"))
+        # shard `rank` of target c carries the value 100 c + rank (+ the row index / 1000)
+        audio = torch.stack([100.0 * c + rank + torch.arange(rows) / 1000.0 for c in range(c_total)]).float()
+        for w in x.exchange(0, audio):
+            w.wait()
+        for w in x.exchange(1, audio + 0.5, async_op=False) or []:
+            pass
+        ret[rank] = ({c: t.clone().numpy() for c, t in x.result(0).items()},
+                     {c: t.clone().numpy() for c, t in x.result(1).items()}, x.owned, x.rounds)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_per_target_writers_exchange(world):
+    """Target c ends up on rank c % world with the shards of all ranks in rank order (5 targets on 2 and 3 ranks:
+    uneven ownership, a last round in which only some ranks receive)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_xchg_worker, args=(world, port, ret), nprocs=world, join=True)
+    seen = set()
+    for rank in range(world):
+        r0, r1, owned, rounds = ret[rank]
+        assert owned == [c for c in range(5) if c % world == rank] and rounds == -(-5 // world)
+        assert sorted(r0) == owned
+        for c in owned:
+            seen.add(c)
+            want = np.stack([100.0 * c + src + np.arange(37) / 1000.0 for src in range(world)]).astype(np.float32)
+            np.testing.assert_array_equal(r0[c], want)
+            np.testing.assert_array_equal(r1[c], (want.astype(np.float64) + 0.5).astype(np.float32))
+    assert seen == set(range(5))
