@@ -37,7 +37,7 @@ SECONDS = 60.0
 OFFSETS = [-3.2e6, -1.1e6, 0.4e6, 2.3e6, 4.1e6]
 BW = 12_500.0
 DEEMPH_US = 300.0
-SM_RESERVE = 0            # multi-GPU runs: SMs kept free of the persistent kernel for NCCL (--sm-reserve; measured: no gain)
+SM_RESERVE = 16           # multi-GPU runs: SMs kept free of the persistent kernel for the NCCL exchange (of 148)
 REQ_CHUNK = 1_048_576
 METRIC = "input complex Msamples/s"
 UNIT = "Msamples/s"
@@ -210,6 +210,8 @@ def main() -> None:
     ap.add_argument("--peer-gather", action="store_true",
                     help="multi-GPU: push the audio into rank 0's memory with copy engines (sharding.PeerGather) "
                          "instead of the NCCL gather")
+    ap.add_argument("--serial-exchange", dest="overlap_exchange", action="store_false",
+                    help="multi-GPU: run the exchange of step k before the kernels of step k+1 instead of under them")
     ap.add_argument("--sm-reserve", type=int, default=int(os.environ.get("IQ2A_BENCH_SM_RESERVE", SM_RESERVE)),
                     help="multi-GPU: SMs kept free of the persistent kernel for the NCCL gather (= NCCL channels)")
     args = ap.parse_args()
@@ -263,10 +265,13 @@ def main() -> None:
     if world > 1:
         # keep stdout to the single JSON line: NCCL's version/info banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        # the audio gather runs on at most SM_RESERVE channels: that many SMs are kept free of the persistent
-        # channel-bank kernel below, so the gather of step k really overlaps the compute of step k+1
-        if args.sm_reserve > 0:
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.sm_reserve))
+        # the exchange of step k runs under the kernels of step k+1: small NCCL CTAs (256 threads) fit next to the
+        # persistent channel-bank kernel on the SMs it leaves free (--sm-reserve); measured on 2/4/8 B200:
+        # 2.71 / 2.75 / 3.16 ms per step, against 2.80 / 2.80 / 3.58 with the exchange serialised behind each step
+        # and 3.46 / 3.41 / 3.22 with NCCL's defaults (profiles/r01_multi_gpu_exchange.md)
+        if args.overlap_exchange:
+            os.environ.setdefault("NCCL_NTHREADS", "256")
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     n_seg = int(round(FS * args.seconds))
@@ -292,13 +297,14 @@ def main() -> None:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             peer = None
-    if world > 1 and peer is None:
+    if world > 1 and peer is None and args.overlap_exchange:
         bank.set_sm_reserve(args.sm_reserve)         # room for the NCCL gather's CTAs next to the persistent kernel
     audio_bufs = None if peer is not None else \
         [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
     # default: per-target writers (sharding.WriterExchange): target c is assembled on rank c % N, balanced exchange
     xchg = sharding.WriterExchange(bank.n_channels, rows, torch.float32, dev) if (world > 1 and peer is None) else None
     step_no = [0]
+    pending = [None, None]
     host_publish = []
 
     def resident_step():
@@ -320,20 +326,29 @@ def main() -> None:
             bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
                                   warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
             return
-        # multi-GPU: everything on one stream, the host runs ahead.  The exchange follows the kernels of its step
-        # (measured: NCCL's CTAs cannot be scheduled next to the persistent channel-bank kernel, and when they can --
-        # reserved SMs, fewer channels -- the two slow each other down by more than the overlap gains), with every
-        # SM and NVLink channel to itself it takes 0.25-0.4 ms of a 2.5 ms step.
+        # multi-GPU: device-side ordering only, the host runs ahead
         with torch.cuda.stream(comp):
+            if args.overlap_exchange and pending[k] is not None:
+                for wk in pending[k]:        # the exchange that last read this buffer (two steps ago)
+                    wk.wait()
             bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
                                         warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows,
                                         stream=comp.cuda_stream)
-            for wk in xchg.exchange(k, audio):
-                wk.wait()                    # orders `comp` behind the collective; does not block the host
+            works = xchg.exchange(k, audio)
+            if args.overlap_exchange:
+                pending[k] = works           # runs on NCCL's stream under the next step's kernels
+            else:
+                for wk in works:
+                    wk.wait()                # orders `comp` behind the collective; does not block the host
 
     def drain():
         if peer is not None:
             peer.flush(step_no[0] - 1, comp)
+        with torch.cuda.stream(comp):
+            for k in range(len(pending)):
+                for wk in pending[k] or ():
+                    wk.wait()
+                pending[k] = None
         comp.synchronize()
 
     def sync_all():
@@ -491,7 +506,8 @@ def main() -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
         "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
-                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_gather": (0 if peer is not None else args.sm_reserve) if world > 1 else 0,
+                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_exchange": (args.sm_reserve if (peer is None and args.overlap_exchange) else 0) if world > 1 else 0,
+                   "exchange_overlapped": bool(world > 1 and peer is None and args.overlap_exchange),
                    "gather": "none" if world == 1 else ("peer-memory push to rank 0 (copy engines)" if peer is not None else "per-target writers: all_to_all_single over NCCL, target c on rank c % N"),
                    "gather_verified": gather_ok,
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
