@@ -37,6 +37,7 @@ import numpy as np
 from . import _lib
 from .bank import ChannelBank, Target
 from .input_formats import probe_wav, resolve_input_format
+from .utils import detect_center_frequency, parse_center_frequency
 from .processing import channel_decimation, choose_mix_sign, design_channel_filter, tune_chunk_size
 
 LOG = logging.getLogger(__name__)
@@ -402,13 +403,10 @@ class IQSliceWriter:
 
 
 # ------------------------------------------------------------------------------------------
-_FREQ_IN_NAME = re.compile(r"(?<![0-9.])(\d{5,11})\s*hz", re.IGNORECASE)
-
-
 def center_frequency_from_filename(path: Path) -> float | None:
-    """SDR++ names captures `baseband_<freq>Hz_<time>.wav`; the benchmark uses `..._fc-<freq>Hz.wav`."""
-    hits = _FREQ_IN_NAME.findall(Path(path).name)
-    return float(hits[0]) if hits else None
+    """SDR++ names captures `baseband_<freq>Hz_<time>.wav`; the benchmark uses `..._fc-<freq>Hz.wav`
+    (utils.detect_center_frequency: tags first, then the largest '<n>[k|M|G]Hz' token of the name)."""
+    return parse_center_frequency(Path(path))
 
 
 class _Progress:
@@ -515,11 +513,12 @@ class ProcessingPipeline:
             raise ValueError("Bandwidth must be positive.")
         center = cfg.center_freq
         if center is None:
-            center = center_frequency_from_filename(Path(cfg.in_path))
-            if center is None:
+            found = detect_center_frequency(Path(cfg.in_path))
+            if found.value is None:
                 raise ValueError("Center frequency not supplied and could not be determined from metadata or "
                                  "filename. Use --fc to provide it explicitly.")
-            cfg.center_freq, cfg.center_freq_source = center, "filename"
+            center = found.value
+            cfg.center_freq, cfg.center_freq_source = center, found.source
 
         decimation, fs_channel = channel_decimation(sample_rate, cfg.fs_ch_target)       # :885-890
         chunk = tune_chunk_size(sample_rate, cfg.chunk_size)                            # :929

@@ -41,7 +41,7 @@ def test_pipeline_five_targets_one_pass(tmp_path, no_ffmpeg):
                            chunk_size=m["chunk"], mix_sign_override=1, output_path=tmp_path / "out.wav")
     # chunk_size is only a lower bound (tune_chunk_size): 10 MS/s -> 4 Mi, i.e. the whole test capture is one chunk
     res = ProcessingPipeline(cfg).run_many()
-    assert len(res) == 5 and cfg.center_freq == fc and cfg.center_freq_source == "filename"
+    assert len(res) == 5 and cfg.center_freq == fc and cfg.center_freq_source == "filename:sdrpp"
     for i, r in enumerate(res):
         g = _cases.load(f"case_b_nfm_10M_t{i}")
         assert r.decimation == 104 and r.mix_sign == 1 and r.output_path.name == f"out_{int(round(r.target_freq))}.wav"
