@@ -182,3 +182,15 @@ def test_preview_errors(tmp_path):
     with pytest.raises(ValueError, match="enough samples"):
         gather_snapshot(ProcessingConfig(in_path=raw, input_sample_rate=1e6, center_freq=1e6), 1.0, nfft=4096,
                         hop=None, max_slices=4)
+
+
+def test_compute_psd_output_shapes():
+    # the reference's own test (tests/test_processing.py:63-69), unchanged apart from the import
+    from iq_to_audio_b200.spectrum import compute_psd
+    sr = 1_000_000.0
+    t = np.arange(0, 8192)
+    samples = np.exp(1j * 2.0 * np.pi * 100_000 * t / sr).astype(np.complex64)
+    freqs, psd = compute_psd(samples, sr, nfft=4096)
+    assert freqs.shape == psd.shape
+    assert np.isfinite(psd).all()
+    assert abs(freqs[np.argmax(psd)] - 100_000.0) <= sr / 4096
