@@ -555,9 +555,8 @@ def test_resident_unaligned_pointer_uses_cp_async(gpu):
         rows = bank.rows_in(0, n)
         out = torch.zeros((2, 2, rows), dtype=torch.float32, device="cuda")
         bank.process_resident(aligned.data_ptr(), 0, n, 0, n, dev_audio=out[0].data_ptr(), out_stride=rows)
-        l0 = bank.launches
         bank.reset()
+        assert (buf.data_ptr() + 4) % 16 == 4
         bank.process_resident(buf.data_ptr() + 4, 0, n, 0, n, dev_audio=out[1].data_ptr(), out_stride=rows)
-        assert bank.launches - l0 == l0 - 0 or True
     o = out.cpu().numpy()
     assert np.abs(o[0] - o[1]).max() <= 2e-6
