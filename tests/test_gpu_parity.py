@@ -560,3 +560,23 @@ def test_resident_unaligned_pointer_uses_cp_async(gpu):
         bank.process_resident(buf.data_ptr() + 4, 0, n, 0, n, dev_audio=out[1].data_ptr(), out_stride=rows)
     o = out.cpu().numpy()
     assert np.abs(o[0] - o[1]).max() <= 2e-6
+
+
+def test_float64_scan_agc_path(gpu, monkeypatch):
+    """IQ2A_PRECISE_SSB=0 puts SSB+AGC channels on the float64-scan AGC (DC-blocker scan, then the data-dependent
+    gain recurrence as a second affine scan with restarts at the reference chunk boundaries).  The reference's AGC
+    is ill-conditioned at audio zero crossings (DESIGN.md section 5), so this path is not held to 1e-4 everywhere;
+    it must agree with the reference on the channel samples, on the chunk structure, and on the audio almost
+    everywhere, and the AM channel next to it must stay within tolerance."""
+    monkeypatch.setenv("IQ2A_PRECISE_SSB", "0")
+    names = ["case_c_20M_am", "case_c_20M_usb", "case_c_20M_lsb"]
+    cat, counts, rms, peaks, gold = _stream(gpu, "case_c_20M_am_ssb", names)
+    _check({k: v[:1] for k, v in cat.items()}, counts, rms[:, :1], peaks[:1], gold[:1])
+    for i in (1, 2):
+        g = gold[i]
+        assert counts == list(g["counts"])
+        assert np.abs(cat["bb"][i] - g["baseband"]).max() <= BB_TOL
+        err = np.abs(cat["clipped"][i] - g["clipped"])
+        assert np.isfinite(cat["audio"][i]).all()
+        assert np.median(err) <= 1e-4 and np.mean(err <= 1e-2) >= 0.9
+        assert np.abs(rms[:, i] - g["rms_dbfs"]).max() <= 0.5
