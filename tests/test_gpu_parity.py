@@ -580,3 +580,36 @@ def test_float64_scan_agc_path(gpu, monkeypatch):
         assert np.isfinite(cat["audio"][i]).all()
         assert np.median(err) <= 1e-4 and np.mean(err <= 1e-2) >= 0.9
         assert np.abs(rms[:, i] - g["rms_dbfs"]).max() <= 0.5
+
+
+def test_edge_inputs_empty_tiny_and_sub_row_calls(gpu):
+    """Empty calls, calls shorter than one decimated row, a capture shorter than the filter: counts follow the
+    reference's rule (rows = multiples of D inside the call) and a later normal call is unaffected."""
+    m, fs, d, tg, gold = _targets(gpu, "case_a_nfm_2p5M", ["case_a_nfm_2p5M"])
+    raw = _cases.raw_input("case_a_nfm_2p5M")
+    g = gold[0]
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=m["chunk"]) as bank:
+        r = bank.process_chunk(raw[:0])
+        assert r.count == 0 and r.audio.shape == (1, 0)
+        pos, audio = 0, []
+        for sz in (1, 0, d - 2, 1, 1, 5, 3 * d, 2):                 # row boundaries crossed one sample at a time
+            r = bank.process_chunk(raw[2 * pos:2 * (pos + sz)])
+            assert r.count == orc.decimated_count(pos, pos + sz, d)
+            audio.append(r.audio.copy())
+            pos += sz
+        r = bank.process_chunk(raw[2 * pos:])
+        audio.append(r.audio.copy())
+        got = np.concatenate(audio, axis=1)[0]
+        assert bank.get_state()[1] == raw.size // 2
+    # NFM has no per-call semantics except the NCO phase wrap (1 ulp of phase per call): same stream as the golden
+    assert got.size == g["audio"].size
+    assert np.abs(got - g["audio"]).max() <= AUDIO_TOL
+    # a capture shorter than the channel filter (6449 taps): only head rows exist
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=m["chunk"]) as bank:
+        r = bank.process_chunk(raw[:2 * 1000], want_baseband=True)
+        plan = orc.TargetPlan(sample_rate=fs, freq_offset=m["targets"][0]["f_off"], mix_sign=int(g["mix_sign"]))
+        x = orc.order_iq(orc.unpack_interleaved(raw[:2000], "pcm_s16le"), "iq")
+        want = orc.run_target(x, plan, m["chunk"])
+        assert r.count == want.audio.size == orc.decimated_count(0, 1000, d)
+        assert np.abs(r.baseband[0] - want.baseband).max() <= BB_TOL
+        assert np.abs(r.audio[0] - want.audio).max() <= AUDIO_TOL
