@@ -575,7 +575,8 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         if ((ch[c].mode == IQ2A_MODE_USB || ch[c].mode == IQ2A_MODE_LSB) && ch[c].agc_enabled) {
             const char* env = std::getenv("IQ2A_PRECISE_SSB");
             const bool off = env && std::strcmp(env, "0") == 0;
-            const size_t fir_smem = (size_t)(32 + vd) * 16 * 8 + (size_t)(vd + 1) * 16 * 8;
+            const size_t qp = (size_t)((vd - 1 + 8) & ~7);            // k_fir_decim_f64: 128 rows + padded history, 16 lanes
+            const size_t fir_smem = (128 + qp) * 16 * 16 + qp * 16 * 8;
             if (!off && fir_smem <= 200 * 1024) {
                 tc[c].precise = 1;
                 b->precise.push_back(c);

@@ -20,7 +20,8 @@
 //                    (the gain restarts at 1.0 every chunk, so chunks are independent), then peak /
 //                    clip / RMS exactly as the scan tail does.
 //
-// Cost: ~65 k DFMA per output sample (ntaps = 32 769) -> ~25 ms per channel for 60 s at 20 MS/s.
+// Cost: ~65 k DFMA per output sample (ntaps = 32 769); measured 18 ms per 10 s of a 20 MS/s capture with two such
+// channels (tools/bench_cfg3.py).
 // Only channels that need it take this path; everything else stays on the float32 transform path.
 #include "common.cuh"
 #include "precise.cuh"
@@ -66,65 +67,99 @@ int launch_mix_exact(const MixExactParams& p, int codec, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Polyphase direct form in float64.  CTA = kFirRows output rows x kFirLanes branch lanes.
+// Polyphase direct form in float64, register-tiled.
 //   s[m] = sum_{p<D} sum_{q<=Q} h[qD - p] * mixed[(m - q) D + p]
 // `mixed` starts at row (row0 - Q): element i <-> n = (row0 - Q) D + i.
+// CTA = kFirGroups row groups x kFirLanes branch lanes; a thread owns ONE branch lane and kFirTile consecutive
+// output rows, so a tap h[q] and a sliding window of kFirTile samples stay in registers: per tap one 16-byte and
+// one 8-byte shared load feed 2*kFirTile DFMAs (the untiled form, one row per thread, was bound by its float ->
+// double conversions and shared loads at ~12 % of the FP64 rate).  Samples are widened to double once, when the
+// tile is staged.  Rows are summed over q in ascending order per lane, lanes combined by shuffles at the end.
 // ---------------------------------------------------------------------------------------
-constexpr int kFirRows = 32;
 constexpr int kFirLanes = 16;
+constexpr int kFirTile = 8;
+constexpr int kFirGroups = 16;
+constexpr int kFirRows = kFirTile * kFirGroups;       // output rows per CTA
 
-__global__ void __launch_bounds__(kFirRows * kFirLanes)
+__global__ void __launch_bounds__(kFirGroups * kFirLanes)
 k_fir_decim_f64(const float2* __restrict__ mixed, const double* __restrict__ taps, int ntaps, int D, int Q,
                 int64_t nrows, float2* __restrict__ out) {
-    extern __shared__ unsigned char sm[];
-    float2* sx = reinterpret_cast<float2*>(sm);                                   // [(kFirRows + Q)][kFirLanes]
-    double* st = reinterpret_cast<double*>(sx + (size_t)(kFirRows + Q) * kFirLanes);   // [Q + 1][kFirLanes]
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int Qp = (Q + kFirTile) & ~(kFirTile - 1);      // taps padded to a multiple of the tile (zeros): Qp >= Q + 1
+    double2* sx = reinterpret_cast<double2*>(sm);                                   // [kFirRows + Qp][kFirLanes]
+    double* st = reinterpret_cast<double*>(sx + (size_t)(kFirRows + Qp) * kFirLanes);   // [Qp][kFirLanes]
     const int lane = threadIdx.x % kFirLanes;
-    const int r = threadIdx.x / kFirLanes;
+    const int g = threadIdx.x / kFirLanes;
     const int64_t m0 = (int64_t)blockIdx.x * kFirRows;       // first output row of this CTA (relative)
-    double ar = 0.0, ai = 0.0;
+    double ar[kFirTile], ai[kFirTile];
+#pragma unroll
+    for (int i = 0; i < kFirTile; ++i) ar[i] = ai[i] = 0.0;
+    // buffer row j <-> output row m0 - Qp + j; `mixed` row 0 is output row -Q, so source row = m0 + j - (Qp - Q)
+    const int64_t src0 = m0 - (Qp - Q);
+    const int64_t src_rows = nrows + Q;                      // rows available in `mixed`
     for (int p0 = 0; p0 < D; p0 += kFirLanes) {
         const int p = p0 + lane;
-        // rows (m0 - Q .. m0 + kFirRows - 1) of branch columns p0..p0+15; buffer row j <-> output row m0 - Q + j
-        for (int j = r; j < kFirRows + Q; j += kFirRows) {
-            float2 v = make_float2(0.f, 0.f);
-            if (p < D) v = mixed[(m0 + j) * (int64_t)D + p];
+        for (int j = g; j < kFirRows + Qp; j += kFirGroups) {
+            const int64_t sr = src0 + j;
+            double2 v = make_double2(0.0, 0.0);
+            if (p < D && sr >= 0 && sr < src_rows) {
+                const float2 f = mixed[sr * (int64_t)D + p];
+                v = make_double2((double)f.x, (double)f.y);
+            }
             sx[j * kFirLanes + lane] = v;
         }
-        for (int q = r; q <= Q; q += kFirRows) {
+        for (int q = g; q < Qp; q += kFirGroups) {
             const int64_t k = (int64_t)q * D - p;
-            st[q * kFirLanes + lane] = (p < D && k >= 0 && k < ntaps) ? taps[k] : 0.0;
+            st[q * kFirLanes + lane] = (p < D && q <= Q && k >= 0 && k < ntaps) ? taps[k] : 0.0;
         }
         __syncthreads();
-        // output row m0 + r uses buffer rows (r + Q - q)
-        const float2* xr = sx + (size_t)(r + Q) * kFirLanes + lane;
-        for (int q = 0; q <= Q; ++q) {
-            const float2 v = xr[-(q * kFirLanes)];
-            const double h = st[q * kFirLanes + lane];
-            ar = fma(h, (double)v.x, ar);
-            ai = fma(h, (double)v.y, ai);
+        // row m0 + T g + i at tap q reads buffer row (T g + i + Qp - q), T = kFirTile; window slot of buffer row j is j mod T
+        const double2* xw = sx + (size_t)(kFirTile * g + Qp) * kFirLanes + lane;     // buffer row of (i = 0, q = 0)
+        double2 c[kFirTile];
+#pragma unroll
+        for (int i = 0; i < kFirTile; ++i) c[i] = xw[i * kFirLanes];                  // rows base .. base+T-1, base % T == 0
+        const double* hp = st + lane;
+        for (int q4 = 0; q4 < Qp; q4 += kFirTile) {
+#pragma unroll
+            for (int u = 0; u < kFirTile; ++u) {
+                const double h = hp[(q4 + u) * kFirLanes];
+#pragma unroll
+                for (int i = 0; i < kFirTile; ++i) {
+                    const double2 v = c[(i - u) & (kFirTile - 1)];
+                    ar[i] = fma(h, v.x, ar[i]);
+                    ai[i] = fma(h, v.y, ai[i]);
+                }
+                // the sample one row further back replaces the one that leaves the window
+                c[(kFirTile - 1 - u) & (kFirTile - 1)] = xw[-(q4 + u + 1) * kFirLanes];
+            }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int off = kFirLanes / 2; off > 0; off >>= 1) {
-        ar += __shfl_xor_sync(0xffffffffu, ar, off);
-        ai += __shfl_xor_sync(0xffffffffu, ai, off);
+    for (int i = 0; i < kFirTile; ++i) {
+#pragma unroll
+        for (int off = kFirLanes / 2; off > 0; off >>= 1) {
+            ar[i] += __shfl_xor_sync(0xffffffffu, ar[i], off);
+            ai[i] += __shfl_xor_sync(0xffffffffu, ai[i], off);
+        }
+        const int64_t m = m0 + kFirTile * g + i;
+        if (lane == 0 && m < nrows) out[m] = make_float2((float)ar[i], (float)ai[i]);
     }
-    if (lane == 0 && m0 + r < nrows) out[m0 + r] = make_float2((float)ar, (float)ai);
 }
 
 int launch_fir_decim_f64(const float2* d_mixed, const double* d_taps, int ntaps, int D, int Q, int64_t nrows,
                          float2* d_out, cudaStream_t st) {
     if (nrows <= 0) return IQ2A_OK;
-    const size_t smem = (size_t)(kFirRows + Q) * kFirLanes * sizeof(float2) + (size_t)(Q + 1) * kFirLanes * sizeof(double);
+    const int Qp = (Q + kFirTile) & ~(kFirTile - 1);
+    const size_t smem = (size_t)(kFirRows + Qp) * kFirLanes * sizeof(double2) + (size_t)Qp * kFirLanes * sizeof(double);
+    if (smem > 220 * 1024) { set_error("channel filter too long for the bit-faithful path (%d history rows)", Q); return IQ2A_ERR_INVALID; }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         IQ2A_CUDA_TRY(cudaFuncSetAttribute(k_fir_decim_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const unsigned grid = (unsigned)((nrows + kFirRows - 1) / kFirRows);
-    k_fir_decim_f64<<<grid, kFirRows * kFirLanes, smem, st>>>(d_mixed, d_taps, ntaps, D, Q, nrows, d_out);
+    k_fir_decim_f64<<<grid, kFirGroups * kFirLanes, smem, st>>>(d_mixed, d_taps, ntaps, D, Q, nrows, d_out);
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }
@@ -153,17 +188,44 @@ __device__ __forceinline__ float dc_step(float x, float x1, float y1, bool first
 
 constexpr int kSeqWarm = 8192;
 
-// pass A: one thread per (chunk, channel): DC blocker over the chunk's rows from a speculative start
-__global__ void k_seq_dc(const SeqParams p) {
-    const int kc = blockIdx.x * blockDim.x + threadIdx.x;     // local chunk index
+// The float32 recurrences are run by one WARP per (chunk, channel): the lanes load 32 consecutive rows at once
+// (coalesced, and whatever does not depend on the carried value -- input differences, the AGC's target/|x| division --
+// is computed lane-parallel), then all lanes step through the 32 dependent updates together, fetching row j's term by
+// shuffle; lane j keeps the j-th result for a coalesced store.  One thread walking the rows alone spent ~350 cycles
+// per row waiting for its own loads (8.9 ms per 4 s of capture; 0.3 ms this way).  The arithmetic per row is the
+// same sequence of float32 operations as before.
+
+// rows [a, b) of the DC blocker from state (x1, y1); stores when y_out != nullptr.  All lanes return the same state.
+__device__ __forceinline__ void dc_rows_warp(const float* __restrict__ x, float* __restrict__ y_out, int64_t a, int64_t b,
+                                             float& x1, float& y1) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = a; base < b; base += 32) {
+        const int64_t r = base + lane;
+        const int cnt = (int)min((int64_t)32, b - base);
+        const float xv = r < b ? x[r] : 0.f;
+        float xprev = __shfl_up_sync(0xffffffffu, xv, 1);
+        if (lane == 0) xprev = x1;
+        const float diff = __fsub_rn(xv, xprev);
+        float mine = 0.f;
+        for (int j = 0; j < cnt; ++j) {
+            const float dj = __shfl_sync(0xffffffffu, diff, j);
+            y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
+            if (lane == j) mine = y1;
+        }
+        if (y_out && r < b) y_out[r] = mine;
+        x1 = __shfl_sync(0xffffffffu, xv, cnt - 1);
+    }
+}
+
+// pass A: one warp per (chunk, channel): DC blocker over the chunk's rows from a speculative start
+__global__ void __launch_bounds__(32) k_seq_dc(const SeqParams p) {
+    const int kc = blockIdx.x;                                // local chunk index
     const int ci = blockIdx.y;
-    if (kc >= p.nchunks) return;
+    const int lane = threadIdx.x;
     const int c = p.chan_idx[ci];
     int64_t lo, hi;
     chunk_rows(p, p.chunk0 + kc, &lo, &hi);
     SeqChunk& rec = p.rec[(size_t)ci * p.nchunks + kc];
-    rec.lo = lo;
-    rec.hi = hi;
     const float* x = p.pre + (size_t)c * p.work_stride;
     float* y = p.tmp + (size_t)c * p.work_stride;
     float x1, y1;
@@ -176,20 +238,23 @@ __global__ void k_seq_dc(const SeqParams p) {
         const int64_t w0 = max((int64_t)0, lo - kSeqWarm);
         x1 = w0 > 0 ? x[w0 - 1] : (p.fresh ? 0.f : p.state[c].dc_x);
         y1 = (w0 == 0 && !p.fresh) ? p.state[c].dc_y : 0.f;
-        for (int64_t r = w0; r < lo; ++r) {
-            const float xv = x[r];
-            y1 = dc_step(xv, x1, y1, false);
-            x1 = xv;
-        }
+        dc_rows_warp(x, nullptr, w0, lo, x1, y1);
     }
-    rec.y_start = y1;
-    for (int64_t r = lo; r < hi; ++r) {
-        const float xv = x[r];
-        y1 = dc_step(xv, x1, y1, r == lo);
-        y[r] = y1;
+    const float y_start = y1;
+    if (hi > lo) {
+        // first row of the call: r * y1 is a float64 product there (dc_step)
+        const float xv = x[lo];
+        y1 = dc_step(xv, x1, y1, true);
+        if (lane == 0) y[lo] = y1;
         x1 = xv;
+        dc_rows_warp(x, y, lo + 1, hi, x1, y1);
     }
-    rec.y_end = y1;
+    if (lane == 0) {
+        rec.lo = lo;
+        rec.hi = hi;
+        rec.y_start = y_start;
+        rec.y_end = y1;
+    }
 }
 
 // pass B: one thread per channel walks the chunks; a chunk whose speculative start state differs from
@@ -224,33 +289,47 @@ __global__ void k_seq_fix(const SeqParams p) {
     if (p.repaired) atomicAdd(p.repaired, repaired);
 }
 
-// pass C: AGC (ssb.py:67-80) per chunk, then the writer-side peak / clip and the chunk statistic
-__global__ void k_seq_agc(const SeqParams p) {
-    const int kc = blockIdx.x * blockDim.x + threadIdx.x;
+// pass C: AGC (ssb.py:67-80) per chunk, then the writer-side peak / clip and the chunk statistic; one warp per
+// (chunk, channel), see above
+__global__ void __launch_bounds__(32) k_seq_agc(const SeqParams p) {
+    const int kc = blockIdx.x;
     const int ci = blockIdx.y;
-    if (kc >= p.nchunks) return;
+    const int lane = threadIdx.x;
     const int c = p.chan_idx[ci];
     const SeqChunk rec = p.rec[(size_t)ci * p.nchunks + kc];
-    const float* x = p.tmp + (size_t)c * p.work_stride;
+    const float* __restrict__ x = p.tmp + (size_t)c * p.work_stride;
     const float target = (float)p.agc_target, decay = (float)p.agc_decay;
     float gain = 1.0f;                                                   // restarts every call (ssb.py:72)
     float peak = 0.f;
     double ss = 0.0;
-    for (int64_t r = rec.lo; r < rec.hi; ++r) {
-        const float s = x[r];
-        const float mag = fabsf(s);
-        if (mag > 1e-6f) {
-            const float desired = __fdiv_rn(target, mag);
-            gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(desired, gain)));
+    for (int64_t base = rec.lo; base < rec.hi; base += 32) {
+        const int64_t r = base + lane;
+        const int cnt = (int)min((int64_t)32, rec.hi - base);
+        const float sv = r < rec.hi ? x[r] : 0.f;
+        const float mag = fabsf(sv);
+        const bool live = r < rec.hi && mag > 1e-6f;
+        const float desired = live ? __fdiv_rn(target, mag) : 0.f;
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        float mine = 1.0f;
+        for (int j = 0; j < cnt; ++j) {
+            const float dj = __shfl_sync(0xffffffffu, desired, j);
+            if (mask & (1u << j)) gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
+            if (lane == j) mine = gain;
         }
-        const float o = __fmul_rn(s, gain);
-        if (r < p.n_skip) continue;
+        if (r >= rec.hi || r < p.n_skip) continue;
+        const float o = __fmul_rn(sv, mine);
         const int64_t oi = r - p.n_skip;
         if (p.audio) p.audio[(size_t)c * p.out_stride + oi] = o;
         if (p.clipped) p.clipped[(size_t)c * p.out_stride + oi] = fminf(fmaxf(o, -0.99f), 0.99f);
         peak = fmaxf(peak, fabsf(o));
         ss = fma((double)o, (double)o, ss);
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, off));
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (lane != 0) return;
     if (peak > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&p.state[c].peak), __float_as_uint(peak));
     if (p.sumsq) {
         int64_t w = p.chunk0 + kc - p.win_chunk0;
@@ -262,10 +341,10 @@ __global__ void k_seq_agc(const SeqParams p) {
 
 int launch_seq_tail(const SeqParams& p, cudaStream_t st, int64_t* launches) {
     if (p.nprecise <= 0 || p.nchunks <= 0 || p.n <= 0) return IQ2A_OK;
-    const dim3 grid((p.nchunks + 63) / 64, p.nprecise);
-    k_seq_dc<<<grid, 64, 0, st>>>(p);
+    const dim3 grid(p.nchunks, p.nprecise);                   // one warp per (chunk, channel)
+    k_seq_dc<<<grid, 32, 0, st>>>(p);
     k_seq_fix<<<(p.nprecise + 31) / 32, 32, 0, st>>>(p);
-    k_seq_agc<<<grid, 64, 0, st>>>(p);
+    k_seq_agc<<<grid, 32, 0, st>>>(p);
     if (launches) *launches += 3;
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
