@@ -118,6 +118,7 @@ struct iq2a_bank {
 
     float2* d_gtab = nullptr;
     std::vector<int> precise;       // channels on the bit-faithful path (SSB with AGC on)
+    std::vector<FirFftPlan> fir_plans;   // transform form of their float64 channel filter (M == 0: direct form)
     int* d_precise = nullptr;
     float2* d_mixed = nullptr;   size_t mixed_cap = 0;
     SeqChunk* d_rec = nullptr;   size_t rec_cap = 0;
@@ -164,6 +165,7 @@ struct iq2a_bank {
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
+        for (FirFftPlan& pl : fir_plans) fir_fft_plan_destroy(&pl);
         for (cudaEvent_t e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& sl : slot) {
@@ -338,7 +340,8 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     if (!b->precise.empty()) {
         const int D = b->D, Q = b->vd - 1;
         const int64_t batch = std::max<int64_t>(1024, (24LL << 20) / D) & ~(int64_t)31;
-        for (int c : b->precise) {
+        for (size_t pi = 0; pi < b->precise.size(); ++pi) {
+            const int c = b->precise[pi];
             for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
                 const int64_t r1 = std::min(n_rows, r0 + batch);
                 const int64_t rows_pad = (r1 - r0 + 31) & ~(int64_t)31;
@@ -359,9 +362,12 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
                 if ((rc = dev_grow(&b->d_mixed, &b->mixed_cap, (size_t)m.count))) return rc;
                 m.mixed = b->d_mixed;
                 if ((rc = launch_mix_exact(m, b->cfg.codec, a.st))) return rc;
-                if ((rc = launch_fir_decim_f64(b->d_mixed, b->d_taps + b->tap_off[c], (int)b->taps[c].size(), D, Q,
-                                               r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st)))
-                    return rc;
+                if (pi < b->fir_plans.size() && b->fir_plans[pi].M > 0)
+                    rc = launch_fir_fft64(b->fir_plans[pi], b->d_mixed, r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st);
+                else
+                    rc = launch_fir_decim_f64(b->d_mixed, b->d_taps + b->tap_off[c], (int)b->taps[c].size(), D, Q,
+                                              r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st);
+                if (rc) return rc;
                 b->launches += 2;
             }
         }
@@ -625,6 +631,18 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         if ((rc = dev_alloc(&b->d_precise, b->precise.size())) || (rc = dev_alloc(&b->d_repaired, (size_t)1))) { cudaFree(d_wtab); return fail(rc); }
         ok &= cudaMemcpy(b->d_precise, b->precise.data(), b->precise.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(b->d_repaired, 0, sizeof(int)) == cudaSuccess;
+        // "fft": the transform form of the float64 filter (1.4x faster end to end on cfg3's shape, but 1.3e-4 of its
+        // samples round to the neighbouring complex64 -- the polyphase sum cancels ~80 dB of out-of-band signal in
+        // float64 -- and the point of this path is that they do not; the direct form is the default)
+        const char* env = std::getenv("IQ2A_PRECISE_FIR");
+        if (env && std::strcmp(env, "fft") == 0) {
+            b->fir_plans.resize(b->precise.size());
+            for (size_t pi = 0; pi < b->precise.size(); ++pi) {
+                const int c = b->precise[pi];
+                if ((rc = fir_fft_plan_create(&b->fir_plans[pi], b->d_taps + toff[c], tn[c], D, vd - 1, b->stream))) { cudaFree(d_wtab); return fail(rc); }
+                b->launches += 2;
+            }
+        }
     }
     if (!ok) { cudaFree(d_wtab); set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(IQ2A_ERR_CUDA); }
     {

@@ -24,6 +24,7 @@
 // channels (tools/bench_cfg3.py).
 // Only channels that need it take this path; everything else stays on the float32 transform path.
 #include "common.cuh"
+#include "fft64.cuh"
 #include "precise.cuh"
 #include "../../include/iq2a_b200.h"
 
@@ -160,6 +161,133 @@ int launch_fir_decim_f64(const float2* d_mixed, const double* d_taps, int ntaps,
     }
     const unsigned grid = (unsigned)((nrows + kFirRows - 1) / kFirRows);
     k_fir_decim_f64<<<grid, kFirGroups * kFirLanes, smem, st>>>(d_mixed, d_taps, ntaps, D, Q, nrows, d_out);
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Transform form: s = sum_p h_p * x_p per overlap-save block of M rows, x_p[m] = mixed[mD + p], h_p[q] = h[qD - p].
+//   Y[k] = sum_p H_p[k] X_p[k],  H_p = FFT_M(h_p) / M,  rows >= Q of IFFT_M(Y) are exact convolution outputs.
+// One CTA per block: branch columns are transformed eight at a time in shared memory (fft64.cuh), every thread
+// accumulates its bins of Y in registers, then one inverse transform (forward transform of the conjugate).
+// Float64 throughout, so the result rounds to the same complex64 as the direct form and as the reference's own
+// complex128 transform, up to the same ~1e-8 chance per sample of landing on the other side of a rounding boundary.
+// ---------------------------------------------------------------------------------------
+constexpr int kFftCols = 8;
+constexpr int kFftThreads = 512;
+
+__global__ void k_fir_fft_build(const double* __restrict__ taps, int ntaps, int D, int Q, int M,
+                                const double2* __restrict__ tw, double2* __restrict__ H) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)D * M) return;
+    const int p = (int)(i / M), k = (int)(i - (int64_t)p * M);
+    double re = 0.0, im = 0.0;
+    for (int q = 0; q <= Q; ++q) {
+        const int64_t t = (int64_t)q * D - p;
+        if (t < 0 || t >= ntaps) continue;
+        const double2 w = tw[(int)(((int64_t)k * q) & (M - 1))];
+        re = fma(taps[t], w.x, re);
+        im = fma(taps[t], w.y, im);
+    }
+    H[i] = make_double2(re / M, im / M);
+}
+
+template <int M>
+__global__ void __launch_bounds__(kFftThreads) k_fir_fft64(const float2* __restrict__ mixed, const double2* __restrict__ H,
+                                                           const double2* __restrict__ tw, int D, int Q, int64_t nrows,
+                                                           float2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    double2* s = reinterpret_cast<double2*>(sm);                          // [M][kFftCols]
+    constexpr int BPT = M / kFftThreads;                                  // bins per thread
+    constexpr int LOG2M = M == 1024 ? 10 : 9;
+    const int ld = M - Q;
+    const int64_t row0 = (int64_t)blockIdx.x * ld;                         // first `mixed` row of this block
+    const int64_t src_rows = nrows + Q;
+    double2 acc[BPT];
+    int kr[BPT];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        acc[i] = make_double2(0.0, 0.0);
+        kr[i] = bitrev_n(threadIdx.x + i * kFftThreads, LOG2M);
+    }
+    for (int p0 = 0; p0 < D; p0 += kFftCols) {
+        for (int idx = threadIdx.x; idx < M * kFftCols; idx += kFftThreads) {
+            const int j = idx / kFftCols, c = idx % kFftCols;
+            const int p = p0 + c;
+            const int64_t sr = row0 + j;
+            double2 v = make_double2(0.0, 0.0);
+            if (p < D && sr < src_rows) {
+                const float2 f = mixed[sr * (int64_t)D + p];
+                v = make_double2((double)f.x, (double)f.y);
+            }
+            s[idx] = v;
+        }
+        __syncthreads();
+        fft_dif_shared<kFftCols>(s, M, tw, M);                             // X_p[k] at row bitrev(k)
+        const int ncol = min(kFftCols, D - p0);
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int k = threadIdx.x + i * kFftThreads;
+            const double2* xs = s + (size_t)kr[i] * kFftCols;
+            const double2* hs = H + (size_t)p0 * M + k;
+            for (int c = 0; c < ncol; ++c) {
+                const double2 h = hs[(size_t)c * M], x = xs[c];
+                acc[i].x = fma(h.x, x.x, fma(-h.y, x.y, acc[i].x));
+                acc[i].y = fma(h.x, x.y, fma(h.y, x.x, acc[i].y));
+            }
+        }
+        __syncthreads();
+    }
+    // inverse transform: IFFT(Y) = conj(FFT(conj(Y))) (1/M is in H)
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) s[threadIdx.x + i * kFftThreads] = make_double2(acc[i].x, -acc[i].y);
+    __syncthreads();
+    fft_dif_shared<1>(s, M, tw, M);
+    for (int j = Q + threadIdx.x; j < M; j += kFftThreads) {
+        const int64_t m = row0 + (j - Q);
+        if (m < nrows) {
+            const double2 v = s[bitrev_n(j, LOG2M)];
+            out[m] = make_float2((float)v.x, (float)(-v.y));
+        }
+    }
+}
+
+int fir_fft_plan_create(FirFftPlan* pl, const double* d_taps, int ntaps, int D, int Q, cudaStream_t st) {
+    *pl = FirFftPlan{};
+    const int M = Q < 96 ? 512 : 1024;                                    // keep at least ~80 % of a block useful
+    if (Q >= M / 2) return IQ2A_OK;                                       // too much history: the direct form is used
+    pl->M = M;
+    pl->Q = Q;
+    pl->D = D;
+    IQ2A_CUDA_TRY(cudaMalloc(&pl->tw, (size_t)M * sizeof(double2)));
+    IQ2A_CUDA_TRY(cudaMalloc(&pl->H, (size_t)D * M * sizeof(double2)));
+    k_fft64_twiddle<<<(M + 255) / 256, 256, 0, st>>>(pl->tw, M);
+    const int64_t total = (int64_t)D * M;
+    k_fir_fft_build<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_taps, ntaps, D, Q, M, pl->tw, pl->H);
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
+void fir_fft_plan_destroy(FirFftPlan* pl) {
+    if (pl->H) cudaFree(pl->H);
+    if (pl->tw) cudaFree(pl->tw);
+    *pl = FirFftPlan{};
+}
+
+int launch_fir_fft64(const FirFftPlan& pl, const float2* d_mixed, int64_t nrows, float2* d_out, cudaStream_t st) {
+    if (nrows <= 0) return IQ2A_OK;
+    const int ld = pl.M - pl.Q;
+    const unsigned grid = (unsigned)((nrows + ld - 1) / ld);
+    const size_t smem = (size_t)pl.M * kFftCols * sizeof(double2);
+    if (pl.M == 1024) {
+        static bool cfg = false;
+        if (!cfg) { IQ2A_CUDA_TRY(cudaFuncSetAttribute(k_fir_fft64<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+        k_fir_fft64<1024><<<grid, kFftThreads, smem, st>>>(d_mixed, pl.H, pl.tw, pl.D, pl.Q, nrows, d_out);
+    } else {
+        static bool cfg = false;
+        if (!cfg) { IQ2A_CUDA_TRY(cudaFuncSetAttribute(k_fir_fft64<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+        k_fir_fft64<512><<<grid, kFftThreads, smem, st>>>(d_mixed, pl.H, pl.tw, pl.D, pl.Q, nrows, d_out);
+    }
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }

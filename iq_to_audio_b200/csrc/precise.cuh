@@ -50,4 +50,15 @@ int launch_fir_decim_f64(const float2* d_mixed, const double* d_taps, int ntaps,
                          float2* d_out, cudaStream_t st);
 int launch_seq_tail(const SeqParams& p, cudaStream_t st, int64_t* launches);
 
+// Transform form of the same float64 channel filter (overlap-save over the D polyphase branches of the mixed
+// signal, M-point float64 transforms): ~20x fewer operations than the direct form, same rounding to complex64.
+struct FirFftPlan {
+    int M = 0, Q = 0, D = 0;
+    double2* H = nullptr;      // [D][M] branch filter spectra / M, natural bin order (device)
+    double2* tw = nullptr;     // [M] exp(-2 pi i k / M) (device)
+};
+int fir_fft_plan_create(FirFftPlan* plan, const double* d_taps, int ntaps, int D, int Q, cudaStream_t st);
+void fir_fft_plan_destroy(FirFftPlan* plan);
+int launch_fir_fft64(const FirFftPlan& plan, const float2* d_mixed, int64_t nrows, float2* d_out, cudaStream_t st);
+
 }  // namespace iq2a

@@ -20,20 +20,13 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fft64.cuh"
 #include "../../include/iq2a_b200.h"
 
 namespace iq2a {
 
 constexpr double kPsdEps = 1e-18;      // _NUMPY_EPS, spectrum.py:12
 constexpr int kSmallMax = 8192;        // largest transform done by one CTA (128 KiB of shared memory)
-
-__global__ void k_spec_twiddle(double2* __restrict__ tw, int n) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double s, c;
-    sincospi(-2.0 * (double)k / (double)n, &s, &c);
-    tw[k] = make_double2(c, s);
-}
 
 // np.hanning(n): 0.5 + 0.5 cos(pi (1 - n + 2 i) / (n - 1)); n == 1 -> 1.0
 __host__ __device__ inline double hann_at(int i, int n) {
@@ -45,50 +38,6 @@ __global__ void k_spec_hann(double* __restrict__ w, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) w[i] = hann_at(i, n);
 }
-
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 mul_neg_i(double2 a) { return make_double2(a.y, -a.x); }
-
-// In-place forward DIF FFT of length n (power of two) on NC interleaved columns: element i of column c lives at
-// s[i*NC + c].  X[k] ends up at index bitrev(k).  tw holds W_T^t for t < T, T a multiple of n.
-template <int NC>
-__device__ void fft_dif_shared(double2* s, int n, const double2* __restrict__ tw, int tw_n) {
-    int len = n;
-    for (; len >= 4; len >>= 2) {
-        const int q = len >> 2;
-        const int qshift = 31 - __clz(q);
-        const int tstep = tw_n / len;
-        for (int t = threadIdx.x; t < (n >> 2) * NC; t += blockDim.x) {
-            const int col = t % NC, b = t / NC;
-            const int blk = b >> qshift, j = b & (q - 1);
-            double2* p = s + (size_t)(blk * len + j) * NC + col;
-            const double2 a0 = p[0], a1 = p[(size_t)q * NC], a2 = p[(size_t)2 * q * NC], a3 = p[(size_t)3 * q * NC];
-            const double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = mul_neg_i(csub(a1, a3));
-            // two radix-2 DIF stages at once: quarters hold k = 0, 2, 1, 3 (mod 4) so the final order is bit reversal
-            p[0] = cadd(b0, b2);
-            p[(size_t)q * NC] = cmul(csub(b0, b2), tw[2 * j * tstep]);
-            p[(size_t)2 * q * NC] = cmul(cadd(b1, b3), tw[j * tstep]);
-            p[(size_t)3 * q * NC] = cmul(csub(b1, b3), tw[3 * j * tstep]);
-        }
-        __syncthreads();
-    }
-    if (len == 2) {
-        for (int t = threadIdx.x; t < (n >> 1) * NC; t += blockDim.x) {
-            const int col = t % NC, b = t / NC;
-            double2* p = s + (size_t)(2 * b) * NC + col;
-            const double2 u = p[0], v = p[NC];
-            p[0] = cadd(u, v);
-            p[NC] = csub(u, v);
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ int bitrev_n(int k, int log2n) { return (int)(__brev((unsigned)k) >> (32 - log2n)); }
 
 struct SpecWin {
     const void* raw;     // device frames; window w starts at frame first + w*hop
@@ -221,7 +170,7 @@ static int plan_init(SpecPlan& pl, int nfft, int device, cudaStream_t st) {
         pl.nc = pl.n1 > 512 ? 8 : 16;
     }
     IQ2A_CUDA_TRY(cudaMalloc(&pl.tw, (size_t)nfft * sizeof(double2)));
-    k_spec_twiddle<<<(nfft + 255) / 256, 256, 0, st>>>(pl.tw, nfft);
+    k_fft64_twiddle<<<(nfft + 255) / 256, 256, 0, st>>>(pl.tw, nfft);
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }
