@@ -18,7 +18,7 @@
 // tensor map cannot describe (row pitch D*4 B must be a multiple of 16 B for TMA).
 //
 // Shared memory: T[256][33] float4 (E.re,O.re,E.im,O.im) 135 168 B | PCM staging 4 x 16 512 B |
-// inverse twiddles 4 KB | pre-broadcast forward twiddles 4 KB | mbarrier.  Block b's PCM rows are
+// twiddles W_512^t 4 KB | mbarrier.  Block b's PCM rows are
 // stored rotated by b rows so that the four blocks of a warp's 32 slots hit different banks.
 #pragma once
 #include <cuda.h>
@@ -42,7 +42,7 @@ struct Geo2 {
     static constexpr int RS = LW + 1;              // tile row stride (float4)
     static constexpr int BPT = 512 / NT;           // spectrum bins per thread in the MAC phase
     static constexpr size_t tile_bytes = (size_t)256 * RS * 16;
-    static constexpr size_t smem = tile_bytes + (size_t)BT * kStageBytes + 512 * sizeof(float2) + 256 * sizeof(float4) + 16;
+    static constexpr size_t smem = tile_bytes + (size_t)BT * kStageBytes + 512 * sizeof(float2) + 16;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +51,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // needs its four source registers contiguous and costs four MOVs per store (seen in the ncu source view)
 __device__ __forceinline__ void sts64(void* dst, unsigned long long v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(smem_u32(dst)), "l"(v) : "memory");
+}
+// The same with a shared-window address and a compile-time byte offset.  ptxas fuses the re / im stores of one tile
+// element ([a + o], [a + o + 8]) into one STS.128 and lines the four source registers up with MOVs.  Both ways of
+// avoiding that were measured on B200 and lost (cfg2, 60 s: fused 2.17 ms; two STS.64 kept apart by a run-time
+// address gap 2.41 ms -- a half-warp then covers every other 8 bytes, a two-way bank conflict; real and imaginary
+// parts in separate halves of the tile row, conflict-free STS.64 and no MOVs, 2.19 ms), so the fused form stays.
+template <int OFF>
+__device__ __forceinline__ void sts64_at(uint32_t addr, unsigned long long v) {
+    asm volatile("st.shared.b64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "l"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ ulonglong2 lds128_at(uint32_t addr) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+%3];" : "=l"(v.x), "=l"(v.y) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long pk_make_u(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
 }
 
 
@@ -104,18 +124,13 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
     float4* T = reinterpret_cast<float4*>(smem_raw);
     unsigned char* stage = smem_raw + G2::tile_bytes;
     float2* tw512 = reinterpret_cast<float2*>(stage + BT * kStageBytes);
-    float4* tw256b = reinterpret_cast<float4*>(tw512 + 512);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tw256b + 256);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw512 + 512);
 
     const int tid = threadIdx.x;
     const int slot = tid % LW, rg = tid / LW;          // 16 row groups either way
     const int b_slot = slot >> 3, pl = slot & 7;
 
     for (int i = tid; i < 512; i += NT) tw512[i] = p.twid[i];
-    for (int i = tid; i < 256; i += NT) {
-        const float2 w = p.twid[2 * i];                       // W_256^i = W_512^{2i} = (cos, -sin)
-        tw256b[i] = make_float4(w.x, w.x, w.y, w.y);
-    }
     if (tid == 0) mbar_init(bar, STG == 0 ? 1 : NT);
     __syncthreads();
 
@@ -131,6 +146,17 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
     const float2 wq = p.twid[kq];                             // W_512^{k'}
     const float2 wc = (BPT == 1 && hb0) ? make_float2(-wq.x, -wq.y) : wq;
     const float2* __restrict__ gp = p.gtab + (BPT == 1 ? tid : r_mac);
+
+    // int16 -> float without the (quarter-rate) I2F unit: flip the sign bit of both halves of a frame word (offset
+    // binary), then PRMT each half under the exponent bytes 0x4B00: the float 8388608 + 32768 + s, and the bias
+    // comes off with one packed add per E/O pair.  Q negation: flip the other 15 bits as well, which is the
+    // offset-binary form of -q - 1, and take one less off.  The exponent bytes come from a register that already
+    // holds such a float (the previous row's; a run-time seed for the first), never from a constant: with a
+    // constant ptxas keeps the PRMT selector in a uniform register and spends a MOV per PRMT bringing it over.
+    const uint32_t qmask = p.q_neg ? 0x7fffu : 0x8000u;
+    const uint32_t xmask = p.iq_swap ? (0x80000000u | qmask) : ((qmask << 16) | 0x8000u);
+    const pk_t bias_i = pk_bc(-8421376.0f), bias_q = pk_bc(p.q_neg ? -8421375.0f : -8421376.0f);
+    const uint32_t exp_seed = 0x4B000000u + ((uint32_t)p.iq_swap >> 8);
 
     for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
         const int blk0 = set * BT;
@@ -189,38 +215,41 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                 const int m2 = rg;
                 const uint32_t* st = reinterpret_cast<const uint32_t*>(stage + b_slot * kStageBytes) + pl;
                 pk_t re[16], im[16];
+                auto unpack = [&](auto swapped) {
+                    constexpr uint32_t sel_lo = 0x7610u, sel_hi = 0x7632u;      // half of a | bytes 2, 3 of b
+                    constexpr uint32_t sel_i = decltype(swapped)::value ? sel_hi : sel_lo;
+                    constexpr uint32_t sel_q = decltype(swapped)::value ? sel_lo : sel_hi;
+                    uint32_t ex = exp_seed;
 #pragma unroll
-                for (int m1 = 0; m1 < 16; ++m1) {
-                    const int row = 32 * m1 + 2 * m2 + b_slot;
-                    uint32_t w0 = st[row * 8], w1 = st[(row + 1) * 8];
-                    if (p.iq_swap) {
-                        w0 = __funnelshift_l(w0, w0, 16);
-                        w1 = __funnelshift_l(w1, w1, 16);
+                    for (int m1 = 0; m1 < 16; ++m1) {
+                        const int row = 32 * m1 + 2 * m2 + b_slot;
+                        const uint32_t w0 = st[row * 8] ^ xmask, w1 = st[(row + 1) * 8] ^ xmask;
+                        const uint32_t i0 = __byte_perm(w0, ex, sel_i), i1 = __byte_perm(w1, ex, sel_i);
+                        const uint32_t q0 = __byte_perm(w0, ex, sel_q), q1 = __byte_perm(w1, ex, sel_q);
+                        ex = i0;
+                        re[m1] = pk_add(pk_make_u(i0, i1), bias_i);
+                        im[m1] = pk_add(pk_make_u(q0, q1), bias_q);
                     }
-                    // int16 -> float without the (quarter-rate) I2F unit: 0x4B00_0000 | (s ^ 0x8000) is the
-                    // float 8388608 + 32768 + s; the bias comes off with one packed add per E/O pair.
-                    const pk_t ui = pk_make(__uint_as_float((w0 & 0xffffu) ^ 0x4B008000u),
-                                            __uint_as_float((w1 & 0xffffu) ^ 0x4B008000u));
-                    const pk_t uq = pk_make(__uint_as_float(__byte_perm(w0, 0x4B00u, 0x5432) ^ 0x8000u),
-                                            __uint_as_float(__byte_perm(w1, 0x4B00u, 0x5432) ^ 0x8000u));
-                    re[m1] = pk_add(ui, pk_bc(-8421376.0f));
-                    im[m1] = p.q_neg ? pk_sub(pk_bc(8421376.0f), uq) : pk_add(uq, pk_bc(-8421376.0f));
-                }
+                };
+                if (p.iq_swap) unpack(std::true_type{});
+                else unpack(std::false_type{});
                 pk_dif<16>(re, im);
-                pk_t* dst = reinterpret_cast<pk_t*>(T) + 2 * (m2 * RS + slot);
+                const uint32_t dst = smem_u32(T) + (m2 * RS + slot) * 16;
                 static_for<16>([&](auto kc) {
                     constexpr int k1 = decltype(kc)::value;
                     pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
                     if constexpr (k1 != 0) {
-                        const float4 w = tw256b[(m2 * k1) & 255];           // (wr, wr, wi, wi), W = wr + j wi
-                        const pk_t wr = pk_make(w.x, w.y), wi = pk_make(w.z, w.w);
+                        // W_256^{m2 k1} = W_512^{2 m2 k1}: an 8-byte load that the two row groups of a warp
+                        // share; ptxas turns the (w, w) pairs into scalar-broadcast operands of the packed ops
+                        const float2 w = tw512[(2 * m2 * k1) & 511];
+                        const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
                         const pk_t nr = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
                         const pk_t ni = pk_fma(xr, wi, pk_mul(xi, wr));
                         xr = nr;
                         xi = ni;
                     }
-                    sts64(dst + 2 * (k1 * 16) * RS, xr);
-                    sts64(dst + 2 * (k1 * 16) * RS + 1, xi);
+                    sts64_at<16 * (k1 * 16) * RS>(dst, xr);
+                    sts64_at<16 * (k1 * 16) * RS + 8>(dst, xi);
                 });
             }
             __syncthreads();
@@ -232,20 +261,19 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
             // ------------- pass 2: 16-point DIF over m2, in place ----------------------------------------
             {
                 const int k1 = rg;
-                ulonglong2* base = reinterpret_cast<ulonglong2*>(T) + (k1 * 16) * RS + slot;
+                const uint32_t col = smem_u32(T) + ((k1 * 16) * RS + slot) * 16;
                 pk_t re[16], im[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const ulonglong2 v = base[i * RS];
+                static_for<16>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const ulonglong2 v = lds128_at<16 * i * RS>(col);
                     re[i] = v.x;
                     im[i] = v.y;
-                }
+                });
                 pk_dif<16>(re, im);
-                pk_t* base64 = reinterpret_cast<pk_t*>(base);
                 static_for<16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
-                    sts64(base64 + 2 * k2 * RS, re[bitrev<16>(k2)]);
-                    sts64(base64 + 2 * k2 * RS + 1, im[bitrev<16>(k2)]);
+                    sts64_at<16 * k2 * RS>(col, re[bitrev<16>(k2)]);
+                    sts64_at<16 * k2 * RS + 8>(col, im[bitrev<16>(k2)]);
                 });
             }
             // G for the first two steps of this tile is requested before the barrier so that the L2 round
@@ -289,7 +317,7 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                         // X[k'] = E + W O, X[k'+256] = E - W O, both bins in one packed register pair
                         const float pr = fmaf(wc.x, v.y, -wc.y * v.w), pi = fmaf(wc.x, v.w, wc.y * v.y);
                         const pk_t xr = pk_make(v.x + pr, v.x - pr), xi = pk_make(v.z + pi, v.z - pi);
-                        const pk_t nxi = pk_make(-v.z - pi, pi - v.z);
+                        const pk_t nxi = xi ^ 0x8000000080000000ull;      // sign flips: off the FMA pipe
 #pragma unroll
                         for (int c = 0; c < CG; ++c) {
                             const pk_t gre = pk_make(g[0][c].x, g[0][c].y), gim = pk_make(g[BPT - 1][c].x, g[BPT - 1][c].y);
