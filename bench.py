@@ -88,7 +88,7 @@ def make_targets():
 # clocks / throttle reasons during the timed region
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period: float = 0.004):
+    def __init__(self, index: int, period: float = 0.001):
         self.period = period
         self.samples: list[int] = []
         self.reasons: set[str] = set()

@@ -260,7 +260,7 @@ def test_stream_case_e_preview_truncation(gpu):
     _check(*_stream(gpu, "case_e_truncated", ["case_e_truncated"], limit=m["max_input_samples"]))
 
 
-@pytest.mark.parametrize("order", ["iq", "qi_inv"])
+@pytest.mark.parametrize("order", ["iq", "qi", "iq_inv", "qi_inv"])
 def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
     """The warp-specialised kernel (generation 3), the TMA / packed-f32x2 kernel (generation 2) and the
     bounds-checked kernel (generation 1) implement the same arithmetic: same capture, ragged call sizes
@@ -270,6 +270,10 @@ def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
     rng = np.random.default_rng(17)
     n = 700_001
     raw = rng.integers(-20_000, 20_000, 2 * n, dtype=np.int16)
+    # both ends of the int16 range on both axes: the bit-level unpack (offset binary, Q negation by
+    # complementing) has to agree with generation 1's plain conversion there too
+    raw[1000:1008] = [-32768, -32768, 32767, 32767, -32768, 32767, 32767, -32768]
+    raw[2 * 350_000:2 * 350_000 + 4] = [-32768, 0, 0, -32768]
     T = gpu["Target"]
     tg = [T(1.0e6, taps, 1, "iq"), T(-2.2e6, taps, -1, "iq"), T(3.05e6, taps, 1, "iq")]
     sizes = [300_000, 3, 101, 104, 250_000, n]
