@@ -210,6 +210,10 @@ def main() -> None:
     ap.add_argument("--peer-gather", action="store_true",
                     help="multi-GPU: push the audio into rank 0's memory with copy engines (sharding.PeerGather) "
                          "instead of the NCCL gather")
+    ap.add_argument("--peer-writers", action="store_true",
+                    help="multi-GPU: per-target writers fed by copy-engine pushes over peer memory (sharding.PeerWriters)")
+    ap.add_argument("--nccl-writers", action="store_true",
+                    help="multi-GPU: per-target writers over NCCL all_to_all_single (sharding.WriterExchange)")
     ap.add_argument("--serial-exchange", dest="overlap_exchange", action="store_false",
                     help="multi-GPU: run the exchange of step k before the kernels of step k+1 instead of under them")
     ap.add_argument("--sm-reserve", type=int, default=int(os.environ.get("IQ2A_BENCH_SM_RESERVE", SM_RESERVE)),
@@ -286,23 +290,37 @@ def main() -> None:
     # two audio slots: the gather of step k (NVLink, rank 0's ingress) runs while step k+1 computes.  Preferred:
     # peer-memory push by copy engines (sharding.PeerGather); fallback: NCCL gather.
     comp = torch.cuda.Stream(device=dev)
+    # Multi-GPU audio collection.  Default: per-target writers (target c is assembled on rank c % N), by whichever
+    # transport is faster on this box, decided in the warm-up by timing a few steps of each (identical decision on
+    # every rank): copy-engine pushes over peer memory (sharding.PeerWriters: no SMs, no NCCL in the data path) or
+    # NCCL all_to_all_single under the next step's kernels on reserved SMs (sharding.WriterExchange).
+    # --peer-writers / --nccl-writers / --peer-gather force one.
     peer = None
-    if world > 1 and args.peer_gather:
+    auto = world > 1 and not (args.peer_gather or args.peer_writers or args.nccl_writers)
+    if world > 1 and not args.nccl_writers:
         try:
-            peer = sharding.PeerGather((bank.n_channels, rows), torch.float32, dev)
+            peer = sharding.PeerGather((bank.n_channels, rows), torch.float32, dev) if args.peer_gather else \
+                sharding.PeerWriters(bank.n_channels, rows, torch.float32, dev)
         except Exception as exc:                      # symmetric memory unavailable on this box / build
-            print(f"[bench] peer-memory gather unavailable ({exc!r}); using the NCCL gather", file=sys.stderr)
+            print(f"[bench] peer-memory transport unavailable ({exc!r}); using NCCL", file=sys.stderr)
             peer = None
         ok = torch.tensor([1 if peer is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             peer = None
-    if world > 1 and peer is None and args.overlap_exchange:
-        bank.set_sm_reserve(args.sm_reserve)         # room for the NCCL gather's CTAs next to the persistent kernel
-    audio_bufs = None if peer is not None else \
-        [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
-    # default: per-target writers (sharding.WriterExchange): target c is assembled on rank c % N, balanced exchange
-    xchg = sharding.WriterExchange(bank.n_channels, rows, torch.float32, dev) if (world > 1 and peer is None) else None
+    use_nccl = world > 1 and (peer is None or auto)
+    audio_bufs = [torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
+                  for _ in range(2 if world > 1 else 1)] if (world == 1 or use_nccl) else None
+    xchg = sharding.WriterExchange(bank.n_channels, rows, torch.float32, dev) if use_nccl else None
+    scheme = {"peer": peer is not None}
+
+    def select(use_peer: bool) -> None:
+        scheme["peer"] = use_peer
+        # room for NCCL's CTAs next to the persistent kernel; the copy engines need none
+        bank.set_sm_reserve(args.sm_reserve if (world > 1 and not use_peer and args.overlap_exchange) else 0)
+
+    select(scheme["peer"])
+    peer_no, flushed = [0], [0]
     step_no = [0]
     pending = [None, None]
     host_publish = []
@@ -310,7 +328,9 @@ def main() -> None:
     def resident_step():
         kk = step_no[0]
         step_no[0] += 1
-        if peer is not None:
+        if scheme["peer"]:
+            kk = peer_no[0]
+            peer_no[0] += 1
             audio = peer.slot(kk)
             peer.before_compute(kk, comp)
             bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
@@ -342,8 +362,9 @@ def main() -> None:
                     wk.wait()                # orders `comp` behind the collective; does not block the host
 
     def drain():
-        if peer is not None:
-            peer.flush(step_no[0] - 1, comp)
+        if peer is not None and peer_no[0] > flushed[0]:
+            peer.flush(peer_no[0] - 1, comp)
+            flushed[0] = peer_no[0]
         with torch.cuda.stream(comp):
             for k in range(len(pending)):
                 for wk in pending[k] or ():
@@ -358,19 +379,41 @@ def main() -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
+    calibration = None
+    if auto and peer is not None:
+        calibration = {}
+        for name, use_peer in (("peer_writers_ms", True), ("nccl_writers_ms", False)):
+            select(use_peer)
+            for _ in range(2):
+                resident_step()
+            sync_all()
+            t_c = time.perf_counter()
+            for _ in range(4):
+                resident_step()
+            drain()
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t_c) * 1e3 / 4], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            calibration[name] = float(t.item())
+            sync_all()
+        select(calibration["peer_writers_ms"] <= calibration["nccl_writers_ms"])
     for _ in range(warmup):
         resident_step()
     sync_all()
     # what arrived at the writers is what the ranks produced: per-(rank, target) checksums of the last warm-up step
     gather_ok = None
+    via_peer = scheme["peer"]
     if world > 1:
-        last = step_no[0] - 1
-        src = peer.slot(last) if peer is not None else audio_bufs[last % 2]
+        last = (peer_no[0] if via_peer else step_no[0]) - 1
+        src = peer.slot(last) if via_peer else audio_bufs[last % 2]
         mine = src.double().abs().sum(dim=1)                         # [C]
         sums = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(sums, mine)
         sums = torch.stack(sums)                                     # [world, C]
-        if peer is not None:
+        if via_peer and isinstance(peer, sharding.PeerWriters):
+            ok = all(float((blk.double().abs().sum(dim=1) - sums[:, c]).abs().max()) <= 1e-9 * max(1.0, float(sums[:, c].max()))
+                     for c, blk in peer.result(last).items())
+        elif via_peer:
             ok = rank != 0 or all(abs(float(g.double().abs().sum()) - float(sums[r].sum())) <= 1e-9 * max(1.0, float(sums[r].sum()))
                                   for r, g in enumerate(peer.result(last)))
         else:
@@ -506,9 +549,10 @@ def main() -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 NCO phase and audio recurrences)", "data": "synthetic",
         "config": {"workload": workload_name(args.seconds), "samples_per_gpu": n_seg, "chunk": chunk,
-                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_exchange": (args.sm_reserve if (peer is None and args.overlap_exchange) else 0) if world > 1 else 0,
-                   "exchange_overlapped": bool(world > 1 and peer is None and args.overlap_exchange),
-                   "gather": "none" if world == 1 else ("peer-memory push to rank 0 (copy engines)" if peer is not None else "per-target writers: all_to_all_single over NCCL, target c on rank c % N"),
+                   "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "hop": bank.hop, "decimation": d, "parallelism": f"time-shard x{world}", "sm_reserved_for_exchange": (args.sm_reserve if (not via_peer and args.overlap_exchange) else 0) if world > 1 else 0,
+                   "exchange_overlapped": bool(world > 1 and (via_peer or args.overlap_exchange)),
+                   "gather": "none" if world == 1 else ("per-target writers: copy-engine push over peer memory, target c on rank c % N" if (via_peer and isinstance(peer, sharding.PeerWriters)) else "peer-memory push to rank 0 (copy engines)" if via_peer else "per-target writers: all_to_all_single over NCCL, target c on rank c % N"),
+                   "gather_calibration": calibration,
                    "gather_verified": gather_ok,
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,

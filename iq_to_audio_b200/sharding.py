@@ -232,3 +232,110 @@ class PeerGather:
         if self.rank == self.dst and last_step >= 0 and last_step not in self.consumed:
             self._consume(last_step, self.torch.cuda.Event())
             self.side.synchronize()
+
+
+class PeerWriters:
+    """Per-target writers fed over NVLink peer memory by copy engines (no NCCL, no SMs in the data path).
+
+    The ownership rule of `WriterExchange` (target c is assembled on rank c % world) with the transport of
+    `PeerGather`: every rank owns a receive area that all ranks can address (symmetric memory) and, after the
+    kernels of step k, pushes each target's rows straight into their place on that target's writer with one
+    device-to-device copy per target on a side stream.  A writer takes in only its own targets -- (world-1)/world
+    of ONE target per shard instead of everything -- so the many-to-one congestion that sank the push to rank 0 at
+    N = 8 does not arise, and because copy engines do the moving the persistent channel-bank kernel keeps every SM
+    (the NCCL exchange needs 16 of them reserved).  Ordering is PeerGather's, with every owning rank a consumer:
+
+        compute stream :  compute(k) -> wait push(k-1) -> [owner: wait consume(k-2)] -> barrier(k) -> compute(k+1)
+        side stream    :  wait compute(k) -> push(k)          owner: wait barrier(k) -> consume(k-1)
+
+    Once barrier(k) has passed, every push(k-1) has landed everywhere; three slots make reuse strict.
+    """
+
+    DEPTH = 3
+
+    def __init__(self, n_channels: int, rows: int, dtype, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.C, self.rows, self.dtype = int(n_channels), int(rows), dtype
+        self.per_rank = (self.C + self.world - 1) // self.world          # targets a writer can own
+        self.owned = [c for c in range(self.C) if c % self.world == self.rank]
+        depth = self.DEPTH
+        self.local = [torch.empty((self.C, self.rows), dtype=dtype, device=device) for _ in range(depth)]
+        # recv[slot][j][s]: target j * world + rank as produced by shard s (same shape on every rank: symmetric)
+        self.recv = symm.empty((depth, self.per_rank, self.world, self.rows), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.recv, dist.group.WORLD)
+        self.side = torch.cuda.Stream(device=device)
+        self.pushed = {}
+        self.consumed = {}
+        self.consumer = None                    # owners: callable(step, {target: [world, rows]}) on the side stream
+        # where this rank's rows of target c live on the writer of c, per slot
+        self.dest = [[self._place(slot, c) for c in range(self.C)] for slot in range(depth)]
+
+    def _place(self, slot: int, c: int):
+        owner, j = c % self.world, c // self.world
+        off = ((slot * self.per_rank + j) * self.world + self.rank) * self.rows
+        if owner == self.rank:
+            return self.recv[slot, j, self.rank]
+        return self.hdl.get_buffer(owner, (self.rows,), self.dtype, off)
+
+    def slot(self, k: int):
+        return self.local[k % self.DEPTH]
+
+    def before_compute(self, k: int, stream) -> None:
+        ev = self.pushed.pop(k - self.DEPTH, None)
+        if ev is not None:
+            stream.wait_event(ev)
+
+    def publish(self, k: int, stream) -> None:
+        torch = self.torch
+        s = k % self.DEPTH
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            # start with the neighbour's targets so that the writers are not all hit in the same order
+            for i in range(self.C):
+                c = (self.rank + 1 + i) % self.C
+                self.dest[s][c].copy_(self.local[s][c], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.pushed[k] = done
+        prev = self.pushed.get(k - 1)
+        if prev is not None:
+            stream.wait_event(prev)
+        if self.owned:
+            old = self.consumed.pop(k - 2, None)
+            if old is not None:
+                stream.wait_event(old)
+        with torch.cuda.stream(stream):
+            self.hdl.barrier(channel=0)
+        if self.owned and k >= 1:
+            landed = torch.cuda.Event()
+            landed.record(stream)
+            self._consume(k - 1, landed)
+
+    def _consume(self, k: int, after) -> None:
+        torch = self.torch
+        self.side.wait_event(after)
+        with torch.cuda.stream(self.side):
+            if self.consumer is not None:
+                self.consumer(k, self.result(k))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.consumed[k] = ev
+
+    def result(self, k: int) -> dict:
+        """{target: [world, rows]} for the targets this rank writes (rows of shard s in row s)."""
+        s = k % self.DEPTH
+        return {c: self.recv[s, j] for j, c in enumerate(self.owned)}
+
+    def flush(self, last_step: int, stream) -> None:
+        stream.synchronize()
+        self.side.synchronize()
+        self.dist.barrier()
+        if self.owned and last_step >= 0 and last_step not in self.consumed:
+            self._consume(last_step, self.torch.cuda.Event())
+            self.side.synchronize()
