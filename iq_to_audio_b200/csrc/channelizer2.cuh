@@ -237,22 +237,28 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                 const uint32_t dst = smem_u32(T) + (m2 * RS + slot) * 16;
                 static_for<16>([&](auto kc) {
                     constexpr int k1 = decltype(kc)::value;
-                    pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
                     if constexpr (k1 != 0) {
                         // W_256^{m2 k1} = W_512^{2 m2 k1}: an 8-byte load that the two row groups of a warp
                         // share; ptxas turns the (w, w) pairs into scalar-broadcast operands of the packed ops
+                        const pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
                         const float2 w = tw512[(2 * m2 * k1) & 511];
                         const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
-                        const pk_t nr = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
-                        const pk_t ni = pk_fma(xr, wi, pk_mul(xi, wr));
-                        xr = nr;
-                        xi = ni;
+                        re[bitrev<16>(k1)] = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
+                        im[bitrev<16>(k1)] = pk_fma(xr, wi, pk_mul(xi, wr));
                     }
-                    sts64_at<16 * (k1 * 16) * RS>(dst, xr);
-                    sts64_at<16 * (k1 * 16) * RS + 8>(dst, xi);
+                });
+                // the tile is free once every warp has left the previous multiply-accumulate phase; waiting for
+                // that here, with this tile's pass 1 already computed, absorbs the skew between warps
+                __syncthreads();
+                static_for<16>([&](auto kc) {
+                    constexpr int k1 = decltype(kc)::value;
+                    sts64_at<16 * (k1 * 16) * RS>(dst, re[bitrev<16>(k1)]);
+                    sts64_at<16 * (k1 * 16) * RS + 8>(dst, im[bitrev<16>(k1)]);
                 });
             }
             __syncthreads();
+            // (issuing the next tile's copy one barrier earlier, before this thread's stores, was slower: 2.26 vs
+            // 2.17 ms on cfg2 -- the whole CTA then waits for thread 0 at the barrier below)
             if constexpr (STG == 0) {
                 if (tid == 0 && t + 1 < ntiles) issue(t + 1);
             } else {
@@ -287,7 +293,8 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                     if constexpr (BPT == 1) {
                         g[0][c] = __ldg(gp + ((size_t)pn * CG + c) * 512);
                     } else {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(p.gtab) + ((size_t)pn * CG + c) * 256 + r_mac);
+                        // L2 only: a table line is used once per CTA, and the two CTAs of an SM are not in step
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(p.gtab) + ((size_t)pn * CG + c) * 256 + r_mac);
                         g[0][c] = make_float2(v.x, v.y);
                         g[BPT - 1][c] = make_float2(v.z, v.w);
                     }
@@ -355,8 +362,8 @@ k_channelize2(const ChannelizeParams p, const __grid_constant__ CUtensorMap tmap
                         }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();                      // every warp is done reading the tile
 
         // ------------- output spectra -> shared (layout of the shared inverse), inverse, store -------------
         float2* ytile = reinterpret_cast<float2*>(T);
