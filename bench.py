@@ -35,6 +35,9 @@ sys.path.insert(0, str(ROOT))
 FS = 10e6
 SECONDS = 60.0
 OFFSETS = [-3.2e6, -1.1e6, 0.4e6, 2.3e6, 4.1e6]
+# test knob (not the benchmark): fewer targets than ranks exercises writers that own nothing
+if os.environ.get("IQ2A_BENCH_TARGETS"):
+    OFFSETS = OFFSETS[:max(1, int(os.environ["IQ2A_BENCH_TARGETS"]))]
 BW = 12_500.0
 DEEMPH_US = 300.0
 SM_RESERVE = 16           # multi-GPU runs: SMs kept free of the persistent kernel for the NCCL exchange (of 148)
