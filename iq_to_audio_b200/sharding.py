@@ -234,6 +234,13 @@ class PeerGather:
             self.side.synchronize()
 
 
+def writer_place(c: int, shard: int, world: int, per_rank: int, slot: int, rows: int) -> tuple[int, int, int]:
+    """Where shard `shard`'s rows of target c go: (writer rank, index among the writer's targets, element offset into
+    the writer's receive area laid out [slot][per_rank][world][rows])."""
+    owner, j = c % world, c // world
+    return owner, j, ((slot * per_rank + j) * world + shard) * rows
+
+
 class PeerWriters:
     """Per-target writers fed over NVLink peer memory by copy engines (no NCCL, no SMs in the data path).
 
@@ -275,8 +282,7 @@ class PeerWriters:
         self.dest = [[self._place(slot, c) for c in range(self.C)] for slot in range(depth)]
 
     def _place(self, slot: int, c: int):
-        owner, j = c % self.world, c // self.world
-        off = ((slot * self.per_rank + j) * self.world + self.rank) * self.rows
+        owner, j, off = writer_place(c, self.rank, self.world, self.per_rank, slot, self.rows)
         if owner == self.rank:
             return self.recv[slot, j, self.rank]
         return self.hdl.get_buffer(owner, (self.rows,), self.dtype, off)

@@ -138,3 +138,26 @@ def test_per_target_writers_exchange(world):
             np.testing.assert_array_equal(r0[c], want)
             np.testing.assert_array_equal(r1[c], (want.astype(np.float64) + 0.5).astype(np.float32))
     assert seen == set(range(5))
+
+
+def test_writer_place_covers_every_receive_area_exactly_once():
+    """PeerWriters' addressing: for every (slot, target, shard) one place, on the target's writer, no two alike, and
+    all inside the symmetric allocation [depth][per_rank][world][rows] -- for target counts below, equal to and above
+    the number of ranks (writers that own nothing, one, several targets)."""
+    from iq_to_audio_b200.sharding import writer_place
+    rows, depth = 7, 3
+    for world in (2, 3, 4, 8):
+        for C in (1, 3, 5, 8, 11):
+            per_rank = (C + world - 1) // world
+            seen = {r: set() for r in range(world)}
+            for slot in range(depth):
+                for c in range(C):
+                    for shard in range(world):
+                        owner, j, off = writer_place(c, shard, world, per_rank, slot, rows)
+                        assert owner == c % world and j == c // world and j < per_rank
+                        assert 0 <= off and off + rows <= depth * per_rank * world * rows
+                        assert off % rows == 0 and off not in seen[owner]
+                        seen[owner].add(off)
+            for r in range(world):
+                owned = len([c for c in range(C) if c % world == r])
+                assert len(seen[r]) == depth * owned * world
