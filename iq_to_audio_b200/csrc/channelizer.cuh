@@ -98,15 +98,23 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
         s_base[tid] = phasor_f32(nco_phase(p.phase, c, p.w[c], mg_b * (int64_t)D));
     }
     __syncthreads();
-    for (int idx = tid; idx < NS * ld; idx += NT) {
-        const int r = idx % ld, sy = idx / ld;
+    // one (block, channel) spectrum at a time, rows strided over the threads: no division by the run-time row count,
+    // 32-bit indices inside the row loop, the block / range tests hoisted out of it
+#pragma unroll 1
+    for (int sy = 0; sy < NS; ++sy) {
         const int b = sy / CG, c = sy % CG;
         const int blk = blk0 + b;
-        const int64_t mg = p.mg_begin + (int64_t)blk * ld + r;
-        if (blk < p.nblocks && mg < p.mg_end && c < p.nchan) {
-            const float2 y = tile[(p.vd + r) * YS + sy];
-            const float2 lo = cmul(s_base[sy], __ldg(p.rot + (size_t)c * ld + r));
-            p.out[(size_t)c * p.out_stride + (mg - p.mg_begin)] = cmul(y, lo);
+        if (blk >= p.nblocks || c >= p.nchan) continue;
+        const int64_t row0 = (int64_t)blk * ld;                               // first row of the block, from mg_begin
+        const int64_t left = p.mg_end - p.mg_begin - row0;
+        const int rows = left < (int64_t)ld ? (int)left : ld;
+        const float2 base = s_base[sy];
+        const float2* __restrict__ rot = p.rot + (size_t)c * ld;
+        const float2* __restrict__ col = tile + p.vd * YS + sy;
+        float2* __restrict__ out = p.out + (size_t)c * p.out_stride + row0;
+        for (int r = tid; r < rows; r += NT) {
+            const float2 lo = cmul(base, __ldg(rot + r));
+            out[r] = cmul(col[r * YS], lo);
         }
     }
 }
