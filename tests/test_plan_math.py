@@ -60,3 +60,28 @@ def test_host_helpers_match_oracle():
         np.testing.assert_array_equal(gp.design_channel_filter(fs, bw, d), orc.channel_taps(fs, bw, d))
     with pytest.raises(ValueError):
         gp.design_channel_filter(1e6, -1.0, 10)
+
+
+def test_int16_unpack_bit_trick_is_exact_for_every_value():
+    """The channel bank turns an int16 pair into two floats without an integer-to-float conversion
+    (csrc/channelizer2.cuh): flip the sign bit of each half (offset binary; for a negated Q complement the other
+    15 bits as well), put each half under the exponent bytes 0x4B00 and subtract 8421376 (8421375 for the negated
+    half).  Restated in numpy for all 65 536 values of both halves, all four IQ orders."""
+    v = np.arange(-32768, 32768, dtype=np.int64)
+    lo, hi = np.meshgrid(v[::257], v, indexing="ij")              # every high half against a spread of low halves
+    lo = np.concatenate([lo.ravel(), v, v[::-1]])
+    hi = np.concatenate([hi.ravel(), v[::-1], v])
+    w = ((hi & 0xFFFF) << 16 | (lo & 0xFFFF)).astype(np.uint32)   # frame word: first int16 in the low half
+    for swap in (0, 1):
+        for q_neg in (0, 1):
+            qmask = 0x7FFF if q_neg else 0x8000
+            xmask = np.uint32((0x80000000 | qmask) if swap else ((qmask << 16) | 0x8000))
+            x = w ^ xmask
+            half_lo = (x & np.uint32(0xFFFF)) | np.uint32(0x4B000000)
+            half_hi = (x >> np.uint32(16)) | np.uint32(0x4B000000)
+            i_bits, q_bits = (half_hi, half_lo) if swap else (half_lo, half_hi)
+            re = i_bits.view(np.float32) + np.float32(-8421376.0)
+            im = q_bits.view(np.float32) + np.float32(-8421375.0 if q_neg else -8421376.0)
+            want_i, want_q = (hi, lo) if swap else (lo, hi)
+            np.testing.assert_array_equal(re, want_i.astype(np.float32))
+            np.testing.assert_array_equal(im, (-want_q if q_neg else want_q).astype(np.float32))
