@@ -286,7 +286,8 @@ def main() -> None:
     d, fs_ch, targets = make_targets()
     bank = ChannelBank(FS, d, targets, codec="pcm_s16le", iq_order="iq", ref_chunk=chunk, device=local_rank)
     from iq_to_audio_b200 import sharding
-    seg = sharding.plan_segments(world * n_seg, world, chunk, d, bank.halo, ["nfm"] * len(OFFSETS))[rank]
+    seg = sharding.plan_segments(world * n_seg, world, chunk, d, bank.halo, ["nfm"] * len(OFFSETS),
+                                 sample_rate=FS, deemph_us=300.0)[rank]
     warm_rows, seg_begin, seg_end, first = seg.warmup_rows, seg.begin, seg.end, seg.first_frame
     capture = synth_capture_device(first, seg_end - first + d, dev, seed=1234 + rank)   # + one row of slack
     rows = bank.rows_in(seg_begin, seg_end)
@@ -522,7 +523,7 @@ def main() -> None:
             traffic = traffic * n_in if traffic is not None else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {4: "k_channelize2<5,2>", 3: "k_channelize3<5>", 2: "k_channelize2<5,4>"}.get(bank.kernel_generation, "k_channelize<512,5,s16>"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": {5: "k_channelize5<5>", 4: "k_channelize2<5,2>"}.get(bank.kernel_generation, "k_channelize<512,5,s16>"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_sample": b_alg, "kernel_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1),
                 "peak_source": peak_src}

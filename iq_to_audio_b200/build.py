@@ -66,12 +66,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs.append(o)
         if force or _stale(o, [inst2] + headers):
             jobs.append((inst2, o, [f"-DIQ2A_CG={cg}"]))
-    inst3 = CSRC / "channelizer3_inst.cu"
+    inst5 = CSRC / "channelizer5_inst.cu"
     for cg in GROUP_SIZES:
-        o = OBJ / f"channelizer3_{cg}.o"
+        o = OBJ / f"channelizer5_{cg}.o"
         objs.append(o)
-        if force or _stale(o, [inst3] + headers):
-            jobs.append((inst3, o, [f"-DIQ2A_CG={cg}"]))
+        if force or _stale(o, [inst5] + headers):
+            jobs.append((inst5, o, [f"-DIQ2A_CG={cg}"]))
     # biggest kernels first so the pool drains evenly
     jobs.sort(key=lambda j: -len(j[2]))
 

@@ -94,6 +94,7 @@ struct StreamSlot {
 struct Group {
     int first, count;
     size_t g_off;     // offset (float2 elements) into d_gtab
+    size_t g5_off;    // offset (float4 elements) into d_gtab5
 };
 
 }  // namespace iq2a
@@ -124,6 +125,9 @@ struct iq2a_bank {
     SeqChunk* d_rec = nullptr;   size_t rec_cap = 0;
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
+    float4* d_gtab5 = nullptr;      // mirror-pair table of the generation-5 kernel (channelizer5.cuh)
+    PairGeo pair{};
+    bool pair_ok = false;
     bool v2_ok = false;
     bool cp_ok = false;             // generation 4 with cp.async staging is available (int16, M = 512, any D)
     int kernel_gen = 1;             // 3: warp-specialised kernel, 2: TMA + packed transforms, 1: first generation
@@ -161,7 +165,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -294,7 +298,13 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
             p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
             p.gtab = b->d_gtab2 + g.g_off;
             p.out = b->d_bb + (size_t)g.first * stride;
-            if (use_v2) rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st, b->kernel_gen);
+            if (use_v2 && b->pair_ok) {
+                // kappa^{1/2} = e^{-j w (L-1)/2} of the pair identity joins the output rotation
+                const double half_len = 0.5 * (double)(b->taps[g.first].size() - 1);
+                for (int i = 0; i < g.count; ++i) p.phase_bias[i] = py_fmod(-b->w[g.first + i] * half_len, 2.0 * M_PI);
+                p.gtab = reinterpret_cast<const float2*>(b->d_gtab5 + g.g5_off);
+                rc = launch_channelize5(p, g.count, b->pair, t_base, t_row0, t_rows, b->n_sm, a.st);
+            } else if (use_v2) rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st);
             else rc = launch_channelize2_cp(p, g.count, b->n_sm, a.st);
             if (rc) return rc;
             b->launches++;
@@ -600,7 +610,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     size_t g_total = 0;
     for (int g = 0, first = 0; g < ng; ++g) {
         const int count = C / ng + (g < C % ng ? 1 : 0);
-        b->groups.push_back(Group{first, count, g_total});
+        b->groups.push_back(Group{first, count, g_total, 0});
         g_total += (size_t)D * count * M;
         first += count;
     }
@@ -662,13 +672,30 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     {
         const char* env = std::getenv("IQ2A_CHANNELIZER");
         const bool force_v1 = env && std::strcmp(env, "v1") == 0;
+        const bool force_v4 = env && std::strcmp(env, "v4") == 0;
         const bool bulk = !force_v1 && M == 512 && cfg->codec == IQ2A_CODEC_S16;
         const char* stg = std::getenv("IQ2A_STAGING");               // "cp": cp.async staging even where TMA applies
         b->v2_ok = bulk && D % 4 == 0 && channelize2_available() && !(stg && std::strcmp(stg, "cp") == 0);
-        const int want = (env && std::strcmp(env, "v2") == 0) ? 2 : (env && std::strcmp(env, "v3") == 0) ? 3 : 4;
-        b->cp_ok = bulk && want == 4;
-        b->kernel_gen = b->v2_ok ? want : (b->cp_ok ? 4 : 1);
+        b->cp_ok = bulk;
+        // generation 5 (mirror pairs): every channel the same number of taps, each filter exactly symmetric
+        // (firwin's are, processing.py:613-619), and a rotation that fits the staging geometry
+        bool sym = b->v2_ok && !force_v4;
+        for (int c = 0; c < C && sym; ++c) {
+            sym = tn[c] == tn[0];
+            const std::vector<double>& h = b->taps[c];
+            for (size_t i = 0, n = h.size(); i < n / 2 && sym; ++i) sym = h[i] == h[n - 1 - i];
+        }
+        b->pair_ok = sym && pair_geometry(tn[0], D, &b->pair);
+        b->kernel_gen = b->pair_ok ? 5 : ((b->v2_ok || b->cp_ok) ? 4 : 1);
         if ((b->v2_ok || b->cp_ok) && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
+        if (b->pair_ok) {
+            size_t g5_total = 0;
+            for (Group& g : b->groups) {
+                g.g5_off = g5_total;
+                g5_total += (size_t)pair_table_entries(b->pair) * g.count * 256;
+            }
+            if ((rc = dev_alloc(&b->d_gtab5, g5_total))) { cudaFree(d_wtab); return fail(rc); }
+        }
     }
     for (const Group& g : b->groups)
         for (int i = 0; i < g.count; ++i) {
@@ -677,9 +704,12 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
                                 b->d_gtab + g.g_off, g.count, i, 0, 1.0, b->stream);
             if (!rc && (b->v2_ok || b->cp_ok))
                 rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
-                                    b->d_gtab2 + g.g_off, g.count, i, b->kernel_gen == 4 ? 2 : 1, 1.0 / 32768.0, b->stream);
+                                    b->d_gtab2 + g.g_off, g.count, i, 2, 1.0 / 32768.0, b->stream);
+            if (!rc && b->pair_ok)
+                rc = launch_build_gpair(b->d_taps + toff[c], tn[c], b->w[c], D, vd, d_wtab, b->d_gtab5 + g.g5_off,
+                                        g.count, i, 1.0 / 32768.0, b->pair, b->stream);
             if (rc) { cudaFree(d_wtab); return fail(rc); }
-            b->launches += (b->v2_ok || b->cp_ok) ? 2 : 1;
+            b->launches += 1 + ((b->v2_ok || b->cp_ok) ? 1 : 0) + (b->pair_ok ? 1 : 0);
         }
     b->tap_off = toff;
     if ((rc = dev_alloc(&b->d_rot, (size_t)C * b->ld)) || (rc = launch_build_rot(b->d_w, C, D, b->ld, b->d_rot, b->stream))) {

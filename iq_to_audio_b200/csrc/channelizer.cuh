@@ -95,7 +95,7 @@ __device__ __forceinline__ void inverse_and_store(float2* tile, const float2* tw
     if (tid < NS) {
         const int b = tid / CG, c = tid % CG;
         const int64_t mg_b = p.mg_begin + (int64_t)(blk0 + b) * ld;
-        s_base[tid] = phasor_f32(nco_phase(p.phase, c, p.w[c], mg_b * (int64_t)D));
+        s_base[tid] = phasor_f32(nco_phase(p.phase, c, p.w[c], mg_b * (int64_t)D) + p.phase_bias[c]);
     }
     __syncthreads();
     // one (block, channel) spectrum at a time, rows strided over the threads: no division by the run-time row count,

@@ -9,10 +9,6 @@
 #define IQ2A_CAT(a, b) IQ2A_CAT2(a, b)
 
 namespace iq2a {
-int IQ2A_CAT(launch_channelize2_, IQ2A_CG)(const ChannelizeParams& p, const CUtensorMap& tmap, int64_t tmap_row0,
-                                           int n_sm, cudaStream_t st) {
-    return launch_channelize2_cg<IQ2A_CG, 4>(p, tmap, tmap_row0, n_sm, st);
-}
 int IQ2A_CAT(launch_channelize2b_, IQ2A_CG)(const ChannelizeParams& p, const CUtensorMap& tmap, int64_t tmap_row0,
                                             int n_sm, cudaStream_t st) {
     return launch_channelize2_cg<IQ2A_CG, 2>(p, tmap, tmap_row0, n_sm, st);

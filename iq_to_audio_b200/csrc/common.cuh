@@ -43,7 +43,20 @@ struct ChannelizeParams {
     int64_t out_stride;
     PhaseModel phase;
     double w[kMaxGroup]; // signed NCO increment per channel (rad/sample)
+    double phase_bias[kMaxGroup];   // constant added to the NCO phase of the output rotation (generation 5: -w (L-1)/2)
 };
+
+// Mirror-pair geometry of the generation-5 channel bank (channelizer5.cuh), shared by host and device.
+struct PairGeo {
+    int a;                  // A = ceil((ntaps-1)/D): window rotation of class 1 (class 2: A + 1)
+    int g1, g2;             // aligned 4-column groups of class 1 (columns 0..r-1, r = 4 g1) and class 2 (r..D-1)
+    int tiles1;             // tiles of class 1 = ceil(g1 / 2)
+    int ntiles;             // + ceil(g2 / 2)
+    int dm[2], hw[2], hl[2];   // per class: mirror row offset, rows of the wrap box, rows of a linear box
+};
+
+// table entries of the mirror-pair kernel per channel: 4 per tile + the column left at the end of each class
+inline int pair_table_entries(const PairGeo& g) { return 4 * g.ntiles + 2; }
 
 #define IQ2A_CUDA_TRY(expr)                                                              \
     do {                                                                                 \

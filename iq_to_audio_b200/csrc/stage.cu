@@ -259,6 +259,88 @@ __global__ void __launch_bounds__(256) k_build_g(const double* __restrict__ taps
     }
 }
 
+// Table of the mirror-pair kernel (channelizer5.cuh): one block per table entry e.
+//   e = 4 t + q, q < 3: pair (column 4u + q + 1, column 4w + 3 - q) of tile t = (forward group u, mirror group w);
+//                       weight 1/2 when the column is its own mirror, 0 when the pair was already taken (u == w)
+//   e = 4 t + 3:        column 4u with the spectrum carried from the previous tile (or nothing: first tile of a class)
+//   e = 4 ntiles + cls: the column left at the end of class cls (its own mirror, staged rotated by Q = A + cls):
+//                       plain complex entry times W^{-Qk}; zero when the class has an odd number of groups
+// The column p of the entry carries g[q] = h[qD - p] e^{-j w (qD - p - (L-1)/2)}  (= kappa^{-1/2} times the
+// unpaired entry); its spectrum a + j b is stored as float4 (a_k', a_k'+256, b_k', b_k'+256) per (e, c, r),
+// r <-> bin k' = (r>>4) + 16 (r&15).
+__global__ void __launch_bounds__(256) k_build_gpair(const double* __restrict__ taps, int ntaps, double w, int D,
+                                                     int qn, const double2* __restrict__ wtab,
+                                                     float4* __restrict__ gout, int cg, int c_in_group, double scale,
+                                                     PairGeo geo) {
+    extern __shared__ double2 s_g[];    // [qn]
+    constexpr int M = 512;
+    const int e = blockIdx.x;
+    int p = 0, rot = 0;
+    double weight = 1.0;
+    if (e < 4 * geo.ntiles) {
+        const int t = e >> 2, q = e & 3;
+        const int cls = t >= geo.tiles1, j = cls ? t - geo.tiles1 : t;
+        const int gl = cls ? geo.g1 : 0, g = cls ? geo.g2 : geo.g1;
+        const int u = gl + j, wg = gl + g - 1 - j;
+        if (q < 3) {
+            const int f = 4 * u + q + 1, m = 4 * wg + 3 - q;
+            p = f;
+            weight = f < m ? 1.0 : (f == m ? 0.5 : 0.0);
+        } else {
+            p = 4 * u;
+        }
+    } else {
+        const int cls = e - 4 * geo.ntiles;
+        const int gl = cls ? geo.g1 : 0, g = cls ? geo.g2 : geo.g1;
+        if (g <= 0 || (g & 1)) weight = 0.0;
+        else {
+            p = 4 * (gl + g / 2);
+            rot = geo.a + cls;
+        }
+    }
+    const double centre = 0.5 * (double)(ntaps - 1);
+    for (int q = threadIdx.x; q < qn; q += blockDim.x) {
+        const int64_t k = (int64_t)q * D - p;
+        double2 g = make_double2(0.0, 0.0);
+        if (weight != 0.0 && k >= 0 && k < ntaps) {
+            double sn, cs;
+            sincos(-w * ((double)k - centre), &sn, &cs);
+            g = make_double2(taps[k] * cs * weight, taps[k] * sn * weight);
+        }
+        s_g[q] = g;
+    }
+    __syncthreads();
+    const double inv_m = scale / (double)M;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const int r = j & 255;
+        const int bin = (r >> 4) + 16 * (r & 15) + 256 * (j >> 8);
+        double ar = 0.0, ai = 0.0;
+        for (int q = 0; q < qn; ++q) {
+            const double2 tw = wtab[(int)(((int64_t)bin * q) % M)];   // exp(-2 pi j bin q / M)
+            const double2 g = s_g[q];
+            ar += g.x * tw.x - g.y * tw.y;
+            ai += g.x * tw.y + g.y * tw.x;
+        }
+        if (rot) {                                                    // times W^{-rot bin} = conj(wtab[rot bin])
+            const double2 tw = wtab[(int)(((int64_t)bin * rot) % M)];
+            const double br = ar * tw.x + ai * tw.y, bi = ai * tw.x - ar * tw.y;
+            ar = br;
+            ai = bi;
+        }
+        float* gf = reinterpret_cast<float*>(gout + ((size_t)e * cg + c_in_group) * 256 + r);
+        gf[j >> 8] = (float)(ar * inv_m);
+        gf[2 + (j >> 8)] = (float)(ai * inv_m);
+    }
+}
+
+int launch_build_gpair(const double* d_taps, int ntaps, double w, int D, int qn, const double2* d_wtab,
+                       float4* d_gout, int cg, int c_in_group, double scale, const PairGeo& geo, cudaStream_t st) {
+    k_build_gpair<<<pair_table_entries(geo), 256, (size_t)qn * sizeof(double2), st>>>(d_taps, ntaps, w, D, qn, d_wtab,
+                                                                                      d_gout, cg, c_in_group, scale, geo);
+    IQ2A_CUDA_TRY(cudaGetLastError());
+    return IQ2A_OK;
+}
+
 // in-block NCO rotation table Q[c][r] = exp(j w_c D r), r < ld
 __global__ void k_build_rot(const double* __restrict__ w, int D, int ld, float2* __restrict__ rot) {
     const int c = blockIdx.y;

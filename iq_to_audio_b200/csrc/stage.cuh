@@ -31,6 +31,8 @@ int launch_build_g(const double* d_taps, int ntaps, double w, int D, int M, int 
                    const double2* d_wtab, float2* d_gout, int cg, int c_in_group, int layout, double scale,
                    cudaStream_t st);
 
+int launch_build_gpair(const double* d_taps, int ntaps, double w, int D, int qn, const double2* d_wtab,
+                       float4* d_gout, int cg, int c_in_group, double scale, const PairGeo& geo, cudaStream_t st);
 int launch_build_rot(const double* d_w, int nchan, int D, int ld, float2* d_rot, cudaStream_t st);
 
 int launch_channelize(const ChannelizeParams& p, int m_fft, int cg, int codec, int n_sm, cudaStream_t st);
@@ -38,6 +40,10 @@ int channelize_max_group(int m_fft);
 bool channelize2_available();
 int launch_channelize2_cp(const ChannelizeParams& p, int cg, int n_sm, cudaStream_t st);
 int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int64_t tmap_row0, int64_t rows,
-                       int n_sm, cudaStream_t st, int generation);
+                       int n_sm, cudaStream_t st);
+// mirror-pair kernel (symmetric taps of one length for every channel of the launch); false: this bank cannot use it
+bool pair_geometry(int ntaps, int D, PairGeo* geo);
+int launch_channelize5(const ChannelizeParams& p, int cg, const PairGeo& geo, const void* base, int64_t tmap_row0,
+                       int64_t rows, int n_sm, cudaStream_t st);
 
 }  // namespace iq2a

@@ -203,3 +203,102 @@ def emulate_block_math(plan: BankPlan, x: np.ndarray, n_out: int, phases: np.nda
             ph = phases[ci][seg] + plan.increments[ci] * (n_glob - seg * chunk)
             out[ci, m_glob[keep]] = y[vd:][keep] * np.exp(1j * ph)
     return out
+
+
+# ---- mirror-pair form (csrc/channelizer5.cuh) -------------------------------------------------------------
+
+@dataclass
+class PairTile:
+    """One tile of the mirror-pair kernel: forward column group ``u`` (columns 4u..4u+3) and mirror group ``w``
+    (columns 4w..4w+3, block window rotated circularly by ``rot`` rows).  Column 4u+i mirrors column 4w+4-i
+    (i = 1, 2, 3); column 4u mirrors column 4(w+1), which the PREVIOUS tile of the class carried over."""
+    u: int
+    w: int
+    rot: int
+    cls: int
+    first: bool                       # first tile of its class: nothing carried
+    last: bool                        # last tile of its class: column 4w is left over (its own mirror)
+
+
+def pair_tiles(ntaps: int, decimation: int) -> tuple[list[PairTile], int, int]:
+    """Tiles of the mirror-pair kernel for symmetric taps h[n] = h[ntaps-1-n] (firwin's, ref processing.py:613).
+
+    With A = ceil((ntaps-1)/D) and r = A*D - (ntaps-1): branch p <= r mirrors r - p (window rotation A, class 0),
+    branch p > r mirrors r + D - p (rotation A + 1, class 1).  The tensor copy moves aligned groups of four
+    columns, hence D % 4 == 0 and (ntaps - 1) % 4 == 0 (then r % 4 == 0).  Returns (tiles, A, r)."""
+    d = decimation
+    if d % 4 or (ntaps - 1) % 4:
+        raise ValueError("the pair kernel needs D % 4 == 0 and (ntaps - 1) % 4 == 0")
+    a = -(-(ntaps - 1) // d)
+    r = a * d - (ntaps - 1)
+    g1, g2 = r // 4, d // 4 - r // 4
+    tiles: list[PairTile] = []
+    for cls, (gl, g) in enumerate(((0, g1), (g1, g2))):
+        n = (g + 1) // 2
+        for j in range(n):
+            tiles.append(PairTile(u=gl + j, w=gl + g - 1 - j, rot=a + cls, cls=cls, first=j == 0, last=j == n - 1))
+    return tiles, a, r
+
+
+def emulate_block_math_paired(plan: BankPlan, x: np.ndarray, n_out: int, phases: np.ndarray, chunk: int) -> np.ndarray:
+    """numpy model of csrc/channelizer5.cuh (float64): same result as :func:`emulate_block_math`, computed from
+    one REAL-pair table entry (a, b) per branch pair:  Y = kappa^(1/2) * sum_pairs a*(X_p + X~_p') + j*b*(X_p - X~_p')
+    with  a + j*b = kappa^(-1/2) * G[c, p],  kappa = exp(-j*w*(L-1)),  X~ the transform of the rotated window;
+    the tile / carry / end-of-class schedule is the kernel's."""
+    d, m_fft, vd, ld = plan.decimation, plan.m_fft, plan.vd, plan.ld
+    ntaps = len(plan.channels[0].taps)
+    for ch in plan.channels:
+        h = np.asarray(ch.taps)
+        if len(h) != ntaps or not np.array_equal(h, h[::-1]):
+            raise ValueError("the pair form needs symmetric taps of one length")
+    tiles, _, _ = pair_tiles(ntaps, d)
+    out = np.zeros((plan.n_channels, n_out), dtype=np.complex128)
+    xs = np.asarray(x, dtype=np.complex128)
+    tabs, kap_half = [], []
+    k = np.arange(m_fft)
+    for ci, ch in enumerate(plan.channels):
+        w = plan.increments[ci]
+        g = branch_filters(np.asarray(ch.taps, dtype=np.float64), w, d, m_fft)
+        tabs.append(np.fft.fft(g, axis=1) / m_fft * np.exp(1j * w * (ntaps - 1) / 2.0))
+        kap_half.append(np.exp(-1j * w * (ntaps - 1) / 2.0))
+    nblocks = (n_out + ld - 1) // ld
+    for b in range(nblocks):
+        row0 = b * ld - vd
+        rows = np.zeros((m_fft, d), dtype=np.complex128)
+        lo, hi = row0 * d, (row0 + m_fft) * d
+        src_lo, src_hi = max(lo, 0), min(hi, xs.size)
+        if src_hi > src_lo:
+            rows.reshape(-1)[src_lo - lo:src_hi - lo] = xs[src_lo:src_hi]
+        y_spec = np.zeros((plan.n_channels, m_fft), dtype=np.complex128)
+
+        def pair(entry_col, weight, xf, xm):
+            s, dd = xf + xm, xf - xm
+            for ci in range(plan.n_channels):
+                e = tabs[ci][entry_col] * weight
+                y_spec[ci] += e.real * s + 1j * e.imag * dd
+
+        carried = None
+        for t in tiles:
+            xf = [np.fft.fft(rows[:, 4 * t.u + i]) for i in range(4)]
+            xm = [np.fft.fft(np.roll(rows[:, 4 * t.w + i], t.rot)) for i in range(4)]
+            for i in (1, 2, 3):
+                f, m = 4 * t.u + i, 4 * t.w + 4 - i
+                pair(f, 1.0 if f < m else (0.5 if f == m else 0.0), xf[i], xm[4 - i])
+            pair(4 * t.u, 1.0, xf[0], np.zeros(m_fft) if t.first else carried)
+            if t.last:
+                if t.w != t.u:                                        # an even number of groups: column 4w is left
+                    rot_back = np.exp(2j * np.pi * t.rot * k / m_fft)
+                    for ci in range(plan.n_channels):
+                        y_spec[ci] += tabs[ci][4 * t.w] * rot_back * xm[0]
+                carried = None
+            else:
+                carried = xm[0]
+        for ci in range(plan.n_channels):
+            y = np.fft.ifft(y_spec[ci]) * m_fft * kap_half[ci]
+            m_glob = b * ld + np.arange(ld)
+            keep = m_glob < n_out
+            n_glob = m_glob[keep] * d
+            seg = n_glob // chunk
+            ph = phases[ci][seg] + plan.increments[ci] * (n_glob - seg * chunk)
+            out[ci, m_glob[keep]] = y[vd:][keep] * np.exp(1j * ph)
+    return out

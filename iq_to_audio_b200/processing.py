@@ -53,11 +53,15 @@ def channel_decimation(sample_rate: float, fs_ch_target: float) -> tuple[int, fl
 def design_channel_filter(sample_rate: float, bandwidth: float, decimation: int) -> np.ndarray:
     """Kaiser-windowed low-pass for one channel (ref: processing.py:599-620).  Host-side, once
     per target; uses the same scipy design routine so the taps are bit-identical."""
-    transition = max(1_000.0, 0.5 * bandwidth)
-    edge = min(0.525 * bandwidth, 0.9 * sample_rate / (2.0 * max(decimation, 1)))
+    # every product below is formed in the reference's order of operations: (fs / (2 D)) * 0.9 and 0.9 * fs / (2 D)
+    # differ by one ulp for many (fs, D), and firwin would turn that into different taps
+    transition = max(1_000.0, bandwidth * 0.5)
+    edge = min(bandwidth * 0.5 * 1.05, (sample_rate / (2.0 * max(decimation, 1))) * 0.9)
     if edge <= 0:
         raise ValueError("Invalid cutoff frequency for channel filter.")
-    length = int(np.clip(4.0 / max(transition / sample_rate, 1e-8), 1024, 32768)) | 1
+    length = int(np.clip(4.0 / max(transition / sample_rate, 1e-8), 1024, 32768))
+    if length % 2 == 0:
+        length += 1
     return np.asarray(firwin(length, cutoff=edge, window=("kaiser", kaiser_beta(80.0)), fs=sample_rate),
                       dtype=np.float64)
 

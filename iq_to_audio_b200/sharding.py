@@ -3,7 +3,7 @@
 The path shards by time: rank r owns a contiguous run of reference chunks.  A shard needs
   * a halo of `bank.halo` input samples before its start (the channel filter's history), and
   * a recurrence warm-up of W channel-rate samples started from zero state (de-emphasis and
-    DC blocker are contractions: 0.966^600 and 0.995^4200 are below 1e-9), which costs another
+    DC blocker are contractions; W = ceil(log(1e-9) / log(pole)) from each target's actual pole), which costs another
     (W+1)*D input samples of read-ahead;
 everything else is closed form in the global sample index (NCO phase table, decimation phase,
 AGC restart points, statistics windows), so there is NO data-path collective.  Only the audio
@@ -13,8 +13,12 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-WARMUP_ROWS = {"nfm": 600, "fm": 600, "am": 4200, "usb": 4200, "ssb": 4200, "lsb": 4200,
-               "iq": 0, "none": 0, "pass": 0}
+import math
+
+#: the recurrences a shard restarts from zero state must have forgotten it to this level when its own rows begin
+WARMUP_EPS = 1e-9
+DC_BLOCKER_POLE = 0.995          # ref: decoders/common.py:9
+_NO_STATE = ("iq", "none", "pass")
 
 
 @dataclass(frozen=True)
@@ -36,18 +40,48 @@ class Segment:
         return self.end - self.first_frame
 
 
-def warmup_rows_for(modes) -> int:
-    return max((WARMUP_ROWS[m.lower()] for m in modes), default=0)
+def _mode_of(target) -> str:
+    return (target if isinstance(target, str) else getattr(target, "mode", "nfm")).lower()
 
 
-def plan_segments(n_total: int, world: int, chunk: int, decimation: int, halo: int, modes) -> list[Segment]:
+def warmup_rows_for(targets, *, fs_channel: float = 96_153.846, deemph_us: float = 300.0, eps: float = WARMUP_EPS) -> int:
+    """Channel-rate rows a shard recomputes from zero state before its first own row.
+
+    A first-order recurrence with pole a has forgotten its start after ceil(log(eps) / log(a)) rows, so the count
+    follows the ACTUAL pole of every target: the de-emphasis pole exp(-1 / (fs_channel * tau))
+    (ref: decoders/nfm.py:40-47; 598 rows for 300 us at 96 154 Hz, 1 495 for 750 us, 1 195 at fs_channel 192 kHz)
+    and the DC blocker's 0.995 for AM / SSB (4 135 rows).  `targets` are mode names or objects with `.mode` and
+    optionally `.deemph_us` (bank.Target); the largest requirement wins."""
+    need = 0
+    for t in targets:
+        mode = _mode_of(t)
+        if mode in _NO_STATE:
+            continue
+        if mode in ("nfm", "fm"):
+            tau = max(float(getattr(t, "deemph_us", deemph_us) if not isinstance(t, str) else deemph_us) * 1e-6, 1e-6)
+            pole = math.exp(-1.0 / (float(fs_channel) * tau))
+        elif mode in ("am", "usb", "ssb", "lsb"):
+            pole = DC_BLOCKER_POLE
+        else:
+            raise KeyError(mode)
+        need = max(need, int(math.ceil(math.log(eps) / math.log(pole))))
+    return need
+
+
+def plan_segments(n_total: int, world: int, chunk: int, decimation: int, halo: int, modes, *,
+                  sample_rate: float | None = None, deemph_us: float = 300.0) -> list[Segment]:
     """Split [0, n_total) into `world` contiguous segments whose starts are multiples of the
     reference chunk (AGC restarts and NCO phase wraps then fall where the single-stream run
-    has them).  Trailing ranks may get empty segments when there are fewer chunks than ranks."""
+    has them).  Trailing ranks may get empty segments when there are fewer chunks than ranks.
+
+    `modes`: mode names or Target objects; `sample_rate` (input rate, so fs_channel = sample_rate / decimation)
+    and `deemph_us` size the recurrence warm-up from the targets' real poles (warmup_rows_for); without a
+    sample rate the reference's default channel rate (96 153.846 Hz) is assumed."""
     if world < 1 or chunk < 1 or decimation < 1:
         raise ValueError("world, chunk and decimation must be positive")
     n_chunks = (n_total + chunk - 1) // chunk
-    warm = warmup_rows_for(modes)
+    fs_ch = float(sample_rate) / decimation if sample_rate else 96_153.846
+    warm = warmup_rows_for(modes, fs_channel=fs_ch, deemph_us=deemph_us)
     d = decimation
     segs = []
     for r in range(world):

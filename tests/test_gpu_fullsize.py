@@ -35,7 +35,7 @@ def test_cfg2_full_size_shards_and_oracle_windows():
     raw = bench.synth_capture_device(0, n + d, dev, seed=1)
     assert raw.numel() * 2 > 2**31                                   # the point of this test
     with ChannelBank(fs, d, targets, codec="pcm_s16le", iq_order="iq", ref_chunk=chunk, device=0) as bank:
-        assert bank.kernel_generation == 4
+        assert bank.kernel_generation == 5
         rows = bank.rows_in(0, n)
         assert rows == orc.decimated_count(0, n, d)
         whole = torch.zeros((5, rows), dtype=torch.float32, device=dev)

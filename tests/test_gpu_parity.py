@@ -262,9 +262,9 @@ def test_stream_case_e_preview_truncation(gpu):
 
 @pytest.mark.parametrize("order", ["iq", "qi", "iq_inv", "qi_inv"])
 def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
-    """The warp-specialised kernel (generation 3), the TMA / packed-f32x2 kernel (generation 2) and the
+    """The mirror-pair kernel (generation 5), the unpaired TMA / packed-f32x2 kernel (generation 4) and the
     bounds-checked kernel (generation 1) implement the same arithmetic: same capture, ragged call sizes
-    -> same channel samples."""
+    -> same channel samples.  A filter that is not symmetric cannot be paired and lands on generation 4."""
     fs, d = 10e6, 104
     taps = orc.channel_taps(fs, 12_500.0, d)
     rng = np.random.default_rng(17)
@@ -275,10 +275,10 @@ def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
     raw[1000:1008] = [-32768, -32768, 32767, 32767, -32768, 32767, 32767, -32768]
     raw[2 * 350_000:2 * 350_000 + 4] = [-32768, 0, 0, -32768]
     T = gpu["Target"]
-    tg = [T(1.0e6, taps, 1, "iq"), T(-2.2e6, taps, -1, "iq"), T(3.05e6, taps, 1, "iq")]
     sizes = [300_000, 3, 101, 104, 250_000, n]
 
-    def run():
+    def run(taps):
+        tg = [T(1.0e6, taps, 1, "iq"), T(-2.2e6, taps, -1, "iq"), T(3.05e6, taps, 1, "iq")]
         with gpu["ChannelBank"](fs, d, tg, iq_order=order, ref_chunk=1 << 18, fft_size=512) as bank:
             gen, pos, parts = bank.kernel_generation, 0, []
             for sz in sizes:
@@ -287,18 +287,40 @@ def test_bulk_kernel_equals_first_generation_kernel(gpu, order, monkeypatch):
                     parts.append(bank.process_chunk(raw[2 * pos:2 * e], want_baseband=True).baseband.copy())
                 pos = e
             return gen, np.concatenate(parts, axis=1)
-    gen4, bb4 = run()
-    monkeypatch.setenv("IQ2A_CHANNELIZER", "v3")
-    gen3, bb3 = run()
-    monkeypatch.setenv("IQ2A_CHANNELIZER", "v2")
-    gen2, bb2 = run()
+    gen5, bb5 = run(taps)
+    skew = taps.copy()
+    skew[7] *= 1.0 + 1e-9                                   # no longer exactly symmetric
+    gen4s, _ = run(skew)
+    monkeypatch.setenv("IQ2A_CHANNELIZER", "v4")
+    gen4, bb4 = run(taps)
+    monkeypatch.setenv("IQ2A_CHANNELIZER", "v1")
+    gen1, bb1 = run(taps)
+    assert (gen5, gen4s, gen4, gen1) == (5, 4, 4, 1)
+    assert bb1.shape == bb4.shape == bb5.shape == (3, orc.decimated_count(0, n, d))
+    assert np.abs(bb1 - bb5).max() <= 1e-6 * 20_000 / 32768 * 4
+    assert np.abs(bb1 - bb4).max() <= 1e-6 * 20_000 / 32768 * 4
+
+
+@pytest.mark.parametrize("fs,d,bw", [(2.4e6, 24, 12_500.0), (1.0e6, 12, 10_000.0), (20e6, 208, 10_000.0),
+                                     (61.44e6, 640, 12_500.0), (0.768e6, 8, 12_500.0)])
+def test_mirror_pair_kernel_geometries(gpu, fs, d, bw, monkeypatch):
+    """Generation 5 over the pair geometries of other rates: r = 0 (one class is a single self-paired branch),
+    both classes ragged, long rotations (A = 158) -- against generation 1 on the same random capture."""
+    taps = orc.channel_taps(fs, bw, d)
+    rng = np.random.default_rng(d)
+    n = 40 * 449 * d // 8 + 77
+    raw = rng.integers(-20_000, 20_000, 2 * n, dtype=np.int16)
+    T = gpu["Target"]
+    tg = [T(0.13 * fs, taps, 1, "iq"), T(-0.31 * fs, taps, -1, "iq")]
+
+    def run():
+        with gpu["ChannelBank"](fs, d, tg, ref_chunk=1 << 18, fft_size=512) as bank:
+            return bank.kernel_generation, bank.process_chunk(raw, want_baseband=True).baseband.copy()
+    gen5, bb5 = run()
     monkeypatch.setenv("IQ2A_CHANNELIZER", "v1")
     gen1, bb1 = run()
-    assert (gen4, gen3, gen2, gen1) == (4, 3, 2, 1)
-    assert bb1.shape == bb2.shape == bb3.shape == bb4.shape == (3, orc.decimated_count(0, n, d))
-    assert np.abs(bb1 - bb4).max() <= 1e-6 * 20_000 / 32768 * 4
-    assert np.abs(bb1 - bb2).max() <= 1e-6 * 20_000 / 32768 * 4
-    assert np.abs(bb1 - bb3).max() <= 1e-6 * 20_000 / 32768 * 4
+    assert (gen5, gen1) == (5, 1)
+    assert np.abs(bb1 - bb5).max() <= 1e-6 * 20_000 / 32768 * 4
 
 
 def test_pipelined_stream_equals_synchronous_chunks(gpu):
@@ -435,7 +457,7 @@ def test_cfg4_cfg5_shapes_against_oracle(gpu):
     chunk = 1 << 20
     T = gpu["Target"]
     with gpu["ChannelBank"](fs, d, [T(o, taps, 1, "nfm") for o in offs], ref_chunk=chunk) as bank:
-        assert bank.kernel_generation == 4 and bank.fft_size == 512
+        assert bank.kernel_generation == 5 and bank.fft_size == 512
         parts = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, n)], want_baseband=True) for s in range(0, n, chunk)]
         audio = np.concatenate([p.audio for p in parts], axis=1)
         bb = np.concatenate([p.baseband for p in parts], axis=1)

@@ -80,3 +80,24 @@ def test_oracle_equals_live_reference(ref, seed, fs, mode, bw):
     assert res.peak == float(g["peak"])
     np.testing.assert_array_equal(np.asarray(res.rms_dbfs), g["rms_dbfs"])
     assert res.final["phase"] == float(g["final_phase"]) and res.final["offset"] == int(g["final_offset"])
+
+
+def test_product_filter_design_is_bit_identical_to_the_live_reference(ref):
+    """`iq_to_audio_b200.processing.design_channel_filter` against the reference's own function over a grid of
+    rates, decimations and bandwidths, including the (fs, D) pairs for which (fs/(2D))*0.9 and 0.9*fs/(2D) differ by
+    one ulp and the Nyquist-bound cutoff is the one selected (wide bandwidths) -- ADVICE round 1."""
+    from iq_to_audio_b200 import processing as gp
+    _, proc, _ = ref
+    n_cases = n_bound = 0
+    for fs in (250e3, 1.0e6, 2.4e6, 2.5e6, 5.0e6, 10e6, 20e6, 61.44e6):
+        for d in (1, 2, 3, 13, 26, 104, 208, 640):
+            if fs / d < 8_000.0:
+                continue
+            for bw in (2_800.0, 10_000.0, 12_500.0, 25_000.0, 200_000.0):
+                if (fs / (2.0 * d)) * 0.9 < bw * 0.5 * 1.05:
+                    n_bound += 1
+                want = proc.design_channel_filter(fs, bw, d)
+                np.testing.assert_array_equal(gp.design_channel_filter(fs, bw, d), want)
+                np.testing.assert_array_equal(orc.channel_taps(fs, bw, d), want)
+                n_cases += 1
+    assert n_cases > 100 and n_bound > 20

@@ -85,3 +85,41 @@ def test_int16_unpack_bit_trick_is_exact_for_every_value():
             want_i, want_q = (hi, lo) if swap else (lo, hi)
             np.testing.assert_array_equal(re, want_i.astype(np.float32))
             np.testing.assert_array_equal(im, (-want_q if q_neg else want_q).astype(np.float32))
+
+
+@pytest.mark.parametrize("fs,d,bw", [(10e6, 104, 12_500.0), (2.4e6, 24, 12_500.0), (1.0e6, 12, 10_000.0),
+                                     (0.768e6, 8, 12_500.0), (2.0e6, 20, 12_500.0), (1.6e6, 16, 12_500.0)])
+def test_mirror_pair_form_equals_unpaired_form(fs, d, bw):
+    """The mirror-pair factorisation of csrc/channelizer5.cuh (one real table entry and four multiply-adds per
+    branch PAIR, aligned column groups, one spectrum carried from tile to tile) is an identity for firwin's
+    symmetric taps: same channel samples as the unpaired model -- for r = 0 (no class-1 tiles), even and odd
+    numbers of column groups per class (a middle group that mirrors itself) and single-tile classes."""
+    taps = orc.channel_taps(fs, bw, d)
+    rng = np.random.default_rng(d)
+    n = 3 * 449 * d + 11
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.2
+    chans = [P.ChannelSpec(0.13 * fs, taps, 1), P.ChannelSpec(-0.31 * fs, taps, -1)]
+    pl = P.build_plan(fs, d, chans, m_fft=512)
+    chunk = 1 << 16
+    ph = [P.phase_table(w, chunk, n // chunk + 2) for w in pl.increments]
+    n_out = orc.decimated_count(0, n, d)
+    a = P.emulate_block_math(pl, x, n_out, ph, chunk)
+    b = P.emulate_block_math_paired(pl, x, n_out, ph, chunk)
+    # the only difference is the float32 rounding of the unpaired table (plan.g_table is complex64)
+    assert np.abs(a - b).max() < 2e-7 * np.abs(a).max()
+    tiles, aa, r = P.pair_tiles(len(taps), d)
+    assert aa == -(-(len(taps) - 1) // d) and 0 <= r < d and r % 4 == 0
+    groups = sorted([t.u for t in tiles] + [t.w for t in tiles if t.w != t.u])
+    assert groups == list(range(d // 4))                             # every column group staged exactly once
+
+
+def test_mirror_pair_form_rejects_what_it_cannot_pair():
+    taps = orc.channel_taps(1.0e6, 10_000.0, 12).copy()
+    taps[3] *= 1.0 + 1e-9
+    pl = P.build_plan(1.0e6, 12, [P.ChannelSpec(1e5, taps, 1)], m_fft=512)
+    with pytest.raises(ValueError):
+        P.emulate_block_math_paired(pl, np.zeros(100, complex), 5, [np.zeros(2)], 1 << 16)
+    with pytest.raises(ValueError):
+        P.pair_tiles(1601, 26)                                       # D % 4 != 0: generation 4 takes it
+    with pytest.raises(ValueError):
+        P.pair_tiles(1311, 20)                                       # (ntaps - 1) % 4 != 0

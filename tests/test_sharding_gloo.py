@@ -23,13 +23,23 @@ def test_segment_plan_covers_capture_on_the_chunk_grid():
         assert a.end == b.begin and b.begin % 262_144 == 0 and a.row_end == b.row_begin
     assert segs[0].warmup_rows == 0 and segs[0].first_frame == 0
     for s in segs[1:]:
-        assert s.warmup_rows == 600 and s.first_frame % 4 == 0
-        assert s.first_frame <= (s.row_begin - 600) * 104 - 6_552
+        assert s.warmup_rows == 598 and s.first_frame % 4 == 0          # ceil(log(1e-9) / log(pole)), 300 us at 96 154 Hz
+        assert s.first_frame <= (s.row_begin - 598) * 104 - 6_552
     assert sum(s.rows for s in segs) == orc.decimated_count(0, 10_000_000, 104)
     # fewer chunks than ranks -> empty trailing segments, still a partition
     segs = sharding.plan_segments(300_000, 8, 262_144, 104, 6_552, ["am"])
     assert sum(s.rows for s in segs) == orc.decimated_count(0, 300_000, 104)
-    assert sharding.warmup_rows_for(["nfm", "usb"]) == 4200
+    assert sharding.warmup_rows_for(["nfm", "usb"]) == 4135             # the DC blocker's 0.995 pole
+    # the warm-up follows the real de-emphasis pole: longer time constants and higher channel rates need more rows
+    assert sharding.warmup_rows_for(["nfm"], deemph_us=750.0) == 1495
+    assert sharding.warmup_rows_for(["nfm"], fs_channel=192_000.0) == 1194
+    assert sharding.warmup_rows_for(["iq"]) == 0
+
+    class _T:
+        mode, deemph_us = "nfm", 750.0
+    assert sharding.warmup_rows_for([_T(), "nfm"]) == 1495
+    assert sharding.plan_segments(10_000_000, 2, 262_144, 104, 6_552, ["nfm"], sample_rate=10e6,
+                                  deemph_us=750.0)[1].warmup_rows == 1495
     with pytest.raises(ValueError):
         sharding.plan_segments(10, 0, 1, 1, 0, ["nfm"])
 
@@ -64,16 +74,17 @@ def _oracle_shard(x, seg, plan, chunk):
     return audio[audio.size - seg.rows:]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, deemph_us=300.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         m = _cases.manifest()["case_b_nfm_10M"]
         x = _cases.complex_input("case_b_nfm_10M")
         chunk = m["chunk"]
-        plan = orc.TargetPlan(sample_rate=m["fs"], freq_offset=m["targets"][1]["f_off"], mix_sign=1)
+        plan = orc.TargetPlan(sample_rate=m["fs"], freq_offset=m["targets"][1]["f_off"], mix_sign=1, deemph_us=deemph_us)
         halo = ((len(plan.taps) - 1 + plan.decimation - 1) // plan.decimation + 1) * plan.decimation
-        segs = sharding.plan_segments(x.size, world, chunk, plan.decimation, halo, ["nfm"])
+        segs = sharding.plan_segments(x.size, world, chunk, plan.decimation, halo, ["nfm"], sample_rate=m["fs"],
+                                      deemph_us=deemph_us)
         mine = _oracle_shard(x, segs[rank], plan, chunk)
         local = torch.from_numpy(np.ascontiguousarray(mine)).reshape(1, -1)
         full = sharding.gather_rows(local, segs, dst=0)
@@ -97,6 +108,25 @@ def test_two_rank_time_sharding_reproduces_single_stream():
     assert audio.size == g["audio"].size                      # exact row partition, in order
     assert np.abs(audio - g["audio"]).max() <= 1e-6           # halo + 600-row warm-up: < 1e-8 expected
     assert abs(ret["peak"] - float(g["peak"])) <= 1e-6
+
+
+def test_time_sharding_with_a_long_deemphasis_time_constant():
+    """750 us de-emphasis (pole 0.986): the shard warm-up has to follow the pole (1 495 rows, not the 598 of the
+    300 us default), or every shard after the first starts ~1e-4 off the single-stream run."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret, 750.0), nprocs=2, join=True)
+    m = _cases.manifest()["case_b_nfm_10M"]
+    x = _cases.complex_input("case_b_nfm_10M")
+    plan = orc.TargetPlan(sample_rate=m["fs"], freq_offset=m["targets"][1]["f_off"], mix_sign=1, deemph_us=750.0)
+    want = orc.run_target(x, plan, m["chunk"]).audio
+    assert ret["audio"].size == want.size
+    assert np.abs(ret["audio"] - want).max() <= 1e-7
+    # the old fixed table (600 rows) misses by orders of magnitude more: 0.98675^600 = 3e-4 of the state survives
+    assert 0.98675 ** 600 > 1e-4 and 0.98675 ** 1495 < 3e-9
 
 
 def _xchg_worker(rank, world, port, ret):
