@@ -125,6 +125,7 @@ struct iq2a_bank {
     SeqChunk* d_rec = nullptr;   size_t rec_cap = 0;
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
+    int* d_setctr = nullptr;        // block-set counter of the generation-5 kernel (dynamic scheduling)
     float4* d_gtab5 = nullptr;      // mirror-pair table of the generation-5 kernel (channelizer5.cuh)
     PairGeo pair{};
     bool pair_ok = false;
@@ -165,7 +166,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_setctr, d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -303,6 +304,8 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
                 const double half_len = 0.5 * (double)(b->taps[g.first].size() - 1);
                 for (int i = 0; i < g.count; ++i) p.phase_bias[i] = py_fmod(-b->w[g.first + i] * half_len, 2.0 * M_PI);
                 p.gtab = reinterpret_cast<const float2*>(b->d_gtab5 + g.g5_off);
+                p.set_counter = b->d_setctr;
+                IQ2A_CUDA_TRY(cudaMemsetAsync(b->d_setctr, 0, sizeof(int), a.st));
                 rc = launch_channelize5(p, g.count, b->pair, t_base, t_row0, t_rows, b->n_sm, a.st);
             } else if (use_v2) rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st);
             else rc = launch_channelize2_cp(p, g.count, b->n_sm, a.st);
@@ -694,7 +697,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
                 g.g5_off = g5_total;
                 g5_total += (size_t)pair_table_entries(b->pair) * g.count * 256;
             }
-            if ((rc = dev_alloc(&b->d_gtab5, g5_total))) { cudaFree(d_wtab); return fail(rc); }
+            if ((rc = dev_alloc(&b->d_gtab5, g5_total)) || (rc = dev_alloc(&b->d_setctr, (size_t)1))) { cudaFree(d_wtab); return fail(rc); }
         }
     }
     for (const Group& g : b->groups)

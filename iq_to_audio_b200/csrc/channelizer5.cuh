@@ -41,30 +41,151 @@ struct Geo5 {
     static constexpr int NT = 256, RS = 17;
     static constexpr size_t tile_bytes = (size_t)256 * RS * 16;
     static constexpr size_t orph_bytes = 2 * 256 * 16;           // carried spectrum: [block][row] (E.re, O.re, E.im, O.im)
-    static constexpr size_t smem = tile_bytes + 4 * (size_t)kRegionBytes + orph_bytes + 256 * sizeof(float2) + 16;
+    static constexpr size_t smem = tile_bytes + 4 * (size_t)kRegionBytes + orph_bytes + 256 * sizeof(float2) + 32;
 };
+
+// Epilogue of a block set: inverse 512-point transforms of the CG x 2 output spectra, overlap rows dropped, NCO
+// rotation, complex64 store.  The thread that owns bins (k', k'+256) first does the radix-2 step of the inverse
+//   y[2n'+e] = sum_k' (Y[k'] + (-1)^e Y[k'+256]) W_512^{-e k'} W_256^{-n' k'},
+// which leaves two 256-point inverse transforms per spectrum (even and odd output rows); those ride in the two
+// halves of packed f32x2 registers through two 16-point passes exactly like the forward transforms (the inverse
+// of a packed DIF is the forward DIF with real and imaginary registers exchanged).  Row rho of the result holds
+// output rows 2 rho and 2 rho + 1.  The rotation table entries a thread needs are fixed (rho = thread index), so
+// they are requested before the passes and have landed when the store needs them.
+template <int CG>
+__device__ __forceinline__ void inverse_store5(float4* Y, const float2* tw256, const ChannelizeParams& p, int blk0,
+                                               pk_t (&acc)[2][CG][2], float2 wc, int tid) {
+    constexpr int BT = 2, NS = CG * BT, YS4 = NS + 1, NT = Geo5::NT;
+    static_assert((size_t)(256 * YS4 + 16) * 16 <= Geo5::tile_bytes && 16 * NS <= NT, "layout");
+    auto yaddr = [&](int rho, int sy) { return smem_u32(Y) + (uint32_t)(rho * YS4 + (rho >> 4) + sy) * 16; };
+    __shared__ float2 s_base[kMaxGroup * 2];
+    // ---- radix-2 step on the accumulators, spectra -> shared ------------------------------------------------
+    {
+        const uint32_t dst = yaddr(tid, 0);
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int c = 0; c < CG; ++c) {
+                float r0, r1, i0, i1;
+                pk_split(acc[0][c][b], r0, r1);
+                pk_split(acc[1][c][b], i0, i1);
+                const float dr = r0 - r1, di = i0 - i1;
+                // Z1 = (Y[k'] - Y[k'+256]) * conj(W_512^{k'})
+                const float z1r = fmaf(dr, wc.x, di * wc.y), z1i = fmaf(di, wc.x, -dr * wc.y);
+                const pk_t re = pk_make(r0 + r1, z1r), im = pk_make(i0 + i1, z1i);
+                asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(dst + (b * CG + c) * 16), "l"(re), "l"(im) : "memory");
+            }
+    }
+    // ---- rotation operands of this thread's two output rows, requested now ------------------------------------
+    const int ld = p.ld, r0 = 2 * tid - p.vd;
+    float2 rot_a[CG], rot_b[CG];
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+        const float2* __restrict__ rt = p.rot + (size_t)c * ld;
+        rot_a[c] = (r0 >= 0 && r0 < ld) ? __ldg(rt + r0) : make_float2(0.f, 0.f);
+        rot_b[c] = (r0 + 1 >= 0 && r0 + 1 < ld) ? __ldg(rt + r0 + 1) : make_float2(0.f, 0.f);
+    }
+    if (tid < NS) {
+        const int b = tid / CG, c = tid % CG;
+        const int64_t mg_b = p.mg_begin + (int64_t)(blk0 + b) * ld;
+        s_base[tid] = phasor_f32(nco_phase(p.phase, c, p.w[c], mg_b * (int64_t)p.decim) + p.phase_bias[c]);
+    }
+    __syncthreads();
+    // ---- inverse pass A: 16-point transform over the high bin index a (k' = 16 a + b'), then conj(W_256^{b' alpha}) ----
+    if (tid < 16 * NS) {
+        const int bp = tid & 15, sy = tid >> 4;
+        const uint32_t base = yaddr(bp * 16, sy);
+        pk_t re[16], im[16];
+        static_for<16>([&](auto ac) {
+            constexpr int a = decltype(ac)::value;
+            const ulonglong2 v = lds128_at<16 * a * YS4>(base);
+            re[a] = v.x;
+            im[a] = v.y;
+        });
+        pk_dif<16>(im, re);                   // inverse transform: the forward one on (im, re)
+        static_for<16>([&](auto kc) {
+            constexpr int al = decltype(kc)::value;
+            pk_t xr = re[bitrev<16>(al)], xi = im[bitrev<16>(al)];
+            if constexpr (al != 0) {
+                const float2 w = tw256[al * 16 + bp];
+                const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
+                const pk_t yr = pk_fma(xi, wi, pk_mul(xr, wr));               // x * conj(w)
+                const pk_t yi = pk_sub(pk_mul(xi, wr), pk_mul(xr, wi));
+                xr = yr;
+                xi = yi;
+            }
+            sts64_at<16 * al * YS4>(base, xr);
+            sts64_at<16 * al * YS4 + 8>(base, xi);
+        });
+    }
+    __syncthreads();
+    // ---- inverse pass B: 16-point transform over b' for fixed alpha: row beta*16 + alpha <- y'[alpha + 16 beta] ----
+    if (tid < 16 * NS) {
+        const int al = tid & 15, sy = tid >> 4;
+        const uint32_t base = yaddr(al, sy);
+        pk_t re[16], im[16];
+        static_for<16>([&](auto bc) {
+            constexpr int b = decltype(bc)::value;
+            const ulonglong2 v = lds128_at<16 * (b * 16 * YS4 + b)>(base);
+            re[b] = v.x;
+            im[b] = v.y;
+        });
+        pk_dif<16>(im, re);
+        static_for<16>([&](auto kc) {
+            constexpr int be = decltype(kc)::value;
+            sts64_at<16 * (be * 16 * YS4 + be)>(base, re[bitrev<16>(be)]);
+            sts64_at<16 * (be * 16 * YS4 + be) + 8>(base, im[bitrev<16>(be)]);
+        });
+    }
+    __syncthreads();
+    // ---- drop the overlap rows, rotate by the NCO, store: thread rho writes rows 2 rho - vd and 2 rho - vd + 1 ----
+    const uint32_t src = yaddr(tid, 0);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+        const int blk = blk0 + b;
+        if (blk >= p.nblocks) continue;
+        const int64_t row0 = (int64_t)blk * ld;
+        const int64_t left = p.mg_end - p.mg_begin - row0;
+        const int rows = left < (int64_t)ld ? (int)left : ld;
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+            if (c >= p.nchan) continue;
+            ulonglong2 v;
+            asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(src + (b * CG + c) * 16) : "memory");
+            float ar, br, ai, bi;
+            pk_split(v.x, ar, br);
+            pk_split(v.y, ai, bi);
+            const float2 base = s_base[b * CG + c];
+            float2* __restrict__ out = p.out + (size_t)c * p.out_stride + row0;
+            if (r0 >= 0 && r0 < rows) out[r0] = cmul(make_float2(ar, ai), cmul(base, rot_a[c]));
+            if (r0 + 1 >= 0 && r0 + 1 < rows) out[r0 + 1] = cmul(make_float2(br, bi), cmul(base, rot_b[c]));
+        }
+    }
+}
 
 template <int CG>
 __global__ void __launch_bounds__(Geo5::NT, 2)
 k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, const PairGeo geo, const int64_t tmap_row0) {
     constexpr int RS = Geo5::RS, NT = Geo5::NT, BT = 2;
-    constexpr int NS = CG * BT, YS = NS | 1;
-    static_assert((size_t)512 * YS * sizeof(float2) <= Geo5::tile_bytes, "layout");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* T = reinterpret_cast<float4*>(smem_raw);
     unsigned char* stage = smem_raw + Geo5::tile_bytes;
     unsigned char* orph = stage + 4 * kRegionBytes;
-    float2* tw256 = reinterpret_cast<float2*>(orph + Geo5::orph_bytes);      // W_256^t = W_512^{2t}
+    float2* tw256 = reinterpret_cast<float2*>(orph + Geo5::orph_bytes);      // [k1][m2] = W_256^{m2 k1} = W_512^{2 m2 k1}
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw256 + 256);
+    int* s_ctl = reinterpret_cast<int*>(bar + 1);             // [0]: warps done with the staging buffer, [1]: next block set
 
     const int tid = threadIdx.x;
     const int slot = tid & 15, rg = tid >> 4;
     const int b_slot = slot >> 3, side = (slot >> 2) & 1, col = slot & 3;
     const int m2p1 = (rg + 2 * b_slot) & 15;           // pass-1 row group of this thread (see header: banks)
 
-    tw256[tid] = p.twid[2 * tid];
-    if (tid == 0) mbar_init(bar, 1);
+    tw256[tid] = p.twid[2 * (((tid & 15) * (tid >> 4)) & 255)];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        s_ctl[0] = 0;
+    }
     __syncthreads();
 
     const int nsets = (p.nblocks + BT - 1) / BT;
@@ -87,7 +208,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     const uint32_t* const st_c0 = st_base + (side ? geo.dm[0] : geo.dm[0] + 1) * 4;
     const uint32_t* const st_c1 = st_base + (side ? geo.dm[1] : geo.dm[1] + 1) * 4;
 
-    for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
+    for (int set = blockIdx.x; set < nsets;) {
         const int blk0 = set * BT;
         // acc[0][c][b] = (re_k', re_k'+256), acc[1][c][b] = (im_k', im_k'+256)
         pk_t acc[2][CG][BT];
@@ -98,9 +219,10 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
 #pragma unroll
                 for (int b = 0; b < BT; ++b) acc[h][c][b] = 0ull;
 
-        // The copy of a tile is issued by lane 0 of every warp (12 boxes over 8 warps), so that no warp is held up
-        // for long: thread 0 posts the byte count, warp w takes boxes w and w + 8 of the list
-        //   block b: 3 forward boxes, the wrap box, 2 linear boxes  (b = 0: boxes 0..5, b = 1: boxes 6..11).
+        // The copy of a tile is issued by ONE thread: at the start of a set thread 0, inside the loop lane 0 of the
+        // last warp that has taken its rows out of the staging buffer (a counter in shared memory) -- as early as the
+        // buffer is free, half a pass before the barrier that every warp waits at.
+        //   block b: 3 forward boxes, the wrap box, 2 linear boxes
         auto issue = [&](int t) {
             const int cls = t >= tiles1;
             const int j = cls ? t - tiles1 : t;
@@ -108,27 +230,31 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             const int mir = 4 * ((cls ? geo.g1 + geo.g2 : geo.g1) - 1 - j);                // mirror group w
             const int dm = cls ? geo.dm[1] : geo.dm[0], hw = cls ? geo.hw[1] : geo.hw[0], hl = cls ? geo.hl[1] : geo.hl[0];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(BT * (3 * kFwdBoxRows + hw + 2 * hl) * 16));
-            for (int bx = tid >> 5; bx < 12; bx += 8) {
-                const int b = bx >= 6, k = bx - 6 * b;
+            mbar_expect_tx(bar, (uint32_t)(BT * (3 * kFwdBoxRows + hw + 2 * hl) * 16));
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
                 const int64_t row0 = p.mg_begin + (int64_t)(blk0 + b) * p.ld - p.vd;
                 const int rw = (int)(row0 - tmap_row0);                // tensor row of window row 0
                 unsigned char* rf = stage + (b * 2) * kRegionBytes;
                 unsigned char* rm = rf + kRegionBytes;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    tma_load_2d(rf + k * kFwdBoxRows * 16, &maps.fwd, fwd, rw - (dm + 1) + k * kFwdBoxRows, bar);
                 // (one cp.async.bulk.tensor per descriptor in the source: the descriptor address stays uniform)
-                if (k < 3) tma_load_2d(rf + k * kFwdBoxRows * 16, &maps.fwd, fwd, rw - (dm + 1) + k * kFwdBoxRows, bar);
-                else if (k == 3) {
+                if (cls) {
                     // staging rows [0, hw) <- window rows [512 - hw, 512): rows dm.. are the wrapped part of the rotation
-                    if (cls) tma_load_2d(rm, &maps.wrap[1], mir, rw + 512 - hw, bar);
-                    else tma_load_2d(rm, &maps.wrap[0], mir, rw + 512 - hw, bar);
-                } else {
+                    tma_load_2d(rm, &maps.wrap[1], mir, rw + 512 - hw, bar);
                     // staging rows [hw, hw + 2 hl) <- window rows [0, 2 hl)
-                    if (cls) tma_load_2d(rm + (hw + (k - 4) * hl) * 16, &maps.lin[1], mir, rw + (k - 4) * hl, bar);
-                    else tma_load_2d(rm + (hw + (k - 4) * hl) * 16, &maps.lin[0], mir, rw + (k - 4) * hl, bar);
+                    tma_load_2d(rm + hw * 16, &maps.lin[1], mir, rw, bar);
+                    tma_load_2d(rm + (hw + hl) * 16, &maps.lin[1], mir, rw + hl, bar);
+                } else {
+                    tma_load_2d(rm, &maps.wrap[0], mir, rw + 512 - hw, bar);
+                    tma_load_2d(rm + hw * 16, &maps.lin[0], mir, rw, bar);
+                    tma_load_2d(rm + (hw + hl) * 16, &maps.lin[0], mir, rw + hl, bar);
                 }
             }
         };
-        if ((tid & 31) == 0) issue(0);
+        if (tid == 0) issue(0);
 
         // X[k'] = E + W O, X[k'+256] = E - W O of a packed (E, O) spectrum: both bins in one register pair
         auto radix2 = [&](pk_t e_o_re, pk_t e_o_im, pk_t& xr, pk_t& xi) {
@@ -189,6 +315,9 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                 };
                 if (p.iq_swap) unpack(std::true_type{});
                 else unpack(std::false_type{});
+                // this warp's rows are in registers: the last of the 8 warps to get here starts the next tile's copy
+                __syncwarp();
+                if ((tid & 31) == 0 && t + 1 < ntiles && (atomicAdd(&s_ctl[0], 1) & 7) == 7) issue(t + 1);
                 pk_dif<16>(re, im);
                 const uint32_t dst = smem_u32(T) + (m2p1 * RS + slot) * 16;
                 static_for<16>([&](auto kc) {
@@ -197,15 +326,13 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                         // W_256^{m2 k1}: an 8-byte load that the two row groups of a warp share; ptxas turns the
                         // (w, w) pairs into scalar-broadcast operands of the packed ops
                         const pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
-                        const float2 w = tw256[(m2p1 * k1) & 255];
+                        const float2 w = tw256[k1 * 16 + m2p1];
                         const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
                         re[bitrev<16>(k1)] = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
                         im[bitrev<16>(k1)] = pk_fma(xr, wi, pk_mul(xi, wr));
                     }
                 });
-                __syncthreads();       // the tile is free: every warp has left the previous multiply-accumulate,
-                                       // and every thread has taken its rows out of the staging buffer
-                if ((tid & 31) == 0 && t + 1 < ntiles) issue(t + 1);
+                __syncthreads();       // the tile is free: every warp has left the previous multiply-accumulate
                 static_for<16>([&](auto kc) {
                     constexpr int k1 = decltype(kc)::value;
                     sts64_at<16 * (k1 * 16) * RS>(dst, re[bitrev<16>(k1)]);
@@ -239,7 +366,11 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             float4 g0[CG], g1[CG], g2[CG];
             gload(g0, t * 4);
             gload(g1, t * 4 + 1);
-            __syncthreads();
+            // Row r of the tile is read in the multiply-accumulate phase by thread r and was written in pass 2 by
+            // the 16 threads with the same r >> 4, one column each: the threads of ONE half-warp.  A warp-level
+            // barrier is all this hand-over needs, so the warps of a CTA drift through pass 2 and the
+            // multiply-accumulate phase independently.
+            __syncwarp();
             // ------------- pair butterfly + last radix-2 stage + multiply-accumulate -----------------------
             // slots of block b: forward columns b*8 + 0..3, mirror columns b*8 + 4..7; column i pairs with
             // mirror column 4 - i (i = 1, 2, 3); forward column 0 pairs with the carried spectrum
@@ -288,24 +419,12 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
         }
         __syncthreads();                      // every warp is done reading the tile
 
-        // ------------- output spectra -> shared (layout of the shared inverse), inverse, store -------------
-        float2* ytile = reinterpret_cast<float2*>(T);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int kbin = kq + 256 * h;
-            const int yrow = (kbin & 31) * 16 + (kbin >> 5);      // slot the inverse transform expects
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-#pragma unroll
-                for (int c = 0; c < CG; ++c) {
-                    float re0, re1, im0, im1;
-                    pk_split(acc[0][c][b], re0, re1);
-                    pk_split(acc[1][c][b], im0, im1);
-                    ytile[yrow * YS + b * CG + c] = h == 0 ? make_float2(re0, im0) : make_float2(re1, im1);
-                }
-        }
-        inverse_and_store<512, CG, BT, NT>(ytile, p.twid, p, blk0);
+        // next block set: a global counter when the launch provides one (CTAs run at different speeds: the L2 slice
+        // an SM is close to, the other CTA on the SM), the static stride otherwise
+        if (tid == 0) s_ctl[1] = p.set_counter ? (int)gridDim.x + atomicAdd(p.set_counter, 1) : set + (int)gridDim.x;
+        inverse_store5<CG>(T, tw256, p, blk0, acc, wc, tid);
         __syncthreads();
+        set = s_ctl[1];
     }
 }
 

@@ -43,6 +43,7 @@ struct ChannelizeParams {
     int64_t out_stride;
     PhaseModel phase;
     double w[kMaxGroup]; // signed NCO increment per channel (rad/sample)
+    int* set_counter;    // generation 5: device counter, zero at launch (dynamic block-set scheduling), or null
     double phase_bias[kMaxGroup];   // constant added to the NCO phase of the output rotation (generation 5: -w (L-1)/2)
 };
 
