@@ -174,7 +174,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     unsigned char* orph = stage + 4 * kRegionBytes;
     float2* tw256 = reinterpret_cast<float2*>(orph + Geo5::orph_bytes);      // [k1][m2] = W_256^{m2 k1} = W_512^{2 m2 k1}
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw256 + 256);
-    int* s_ctl = reinterpret_cast<int*>(bar + 1);             // [0]: warps done with the staging buffer, [1]: next block set
+    int* s_ctl = reinterpret_cast<int*>(bar + 1);             // [0]: 8 x tiles taken out of the staging buffer (+ warps of the current one), [1]: next block set
 
     const int tid = threadIdx.x;
     const int slot = tid & 15, rg = tid >> 4;
@@ -189,7 +189,6 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     __syncthreads();
 
     const int nsets = (p.nblocks + BT - 1) / BT;
-    uint32_t parity = 0;
 
     const int r_mac = tid;
     const int kq = (r_mac >> 4) + 16 * (r_mac & 15);          // bin within the 256-point halves
@@ -291,8 +290,9 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
         };
 
         for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(bar, parity);
-            parity ^= 1;
+            // every warp bumps s_ctl[0] once per tile after the wait below, so the tile's sequence number -- and with
+            // it the phase of the barrier -- is s_ctl[0] / 8 for every thread that gets here (no register spent on it)
+            mbar_wait(bar, ((uint32_t)*reinterpret_cast<volatile int*>(s_ctl) >> 3) & 1u);
             // ------------- pass 1: two 16-point DIFs (even / odd rows) per thread, packed ---------------
             {
                 const uint32_t* st = t >= tiles1 ? st_c1 : st_c0;
@@ -317,7 +317,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                 else unpack(std::false_type{});
                 // this warp's rows are in registers: the last of the 8 warps to get here starts the next tile's copy
                 __syncwarp();
-                if ((tid & 31) == 0 && t + 1 < ntiles && (atomicAdd(&s_ctl[0], 1) & 7) == 7) issue(t + 1);
+                if ((tid & 31) == 0 && (atomicAdd(&s_ctl[0], 1) & 7) == 7 && t + 1 < ntiles) issue(t + 1);
                 pk_dif<16>(re, im);
                 const uint32_t dst = smem_u32(T) + (m2p1 * RS + slot) * 16;
                 static_for<16>([&](auto kc) {
@@ -363,7 +363,11 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
 #pragma unroll
                 for (int c = 0; c < CG; ++c) g[c] = __ldcg(gtab + ((size_t)e * CG + c) * 256);
             };
+#ifdef IQ2A_G3SETS
             float4 g0[CG], g1[CG], g2[CG];
+#else
+            float4 g0[CG], g1[CG];
+#endif
             gload(g0, t * 4);
             gload(g1, t * 4 + 1);
             // Row r of the tile is read in the multiply-accumulate phase by thread r and was written in pass 2 by
@@ -375,24 +379,41 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             // slots of block b: forward columns b*8 + 0..3, mirror columns b*8 + 4..7; column i pairs with
             // mirror column 4 - i (i = 1, 2, 3); forward column 0 pairs with the carried spectrum
             const uint32_t trow = smem_u32(T) + r_mac * RS * 16;
+            const bool chain_start = t == 0 || t == tiles1;
+            const bool chain_end = t + 1 == tiles1 || t + 1 == ntiles;
+#ifdef IQ2A_G3SETS
             gload(g2, t * 4 + 2);
             pair_mac(0, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
             pair_mac(1, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
             gload(g0, t * 4 + 3);
             pair_mac(0, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
             pair_mac(1, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
-            const bool chain_start = t == 0 || t == tiles1;
-            const bool chain_end = t + 1 == tiles1 || t + 1 == ntiles;
             if (chain_end) gload(g1, ntiles * 4 + (t + 1 == ntiles ? 1 : 0));
             pair_mac(0, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g2);
             pair_mac(1, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g2);
+            float4 (&g_orph)[CG] = g0;
+            float4 (&g_end)[CG] = g1;
+#else
+            // two table-entry register sets, each reloaded as soon as its step is done (one step ahead)
+            pair_mac(0, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
+            pair_mac(1, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
+            gload(g0, t * 4 + 2);
+            pair_mac(0, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
+            pair_mac(1, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
+            gload(g1, t * 4 + 3);
+            pair_mac(0, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g0);
+            pair_mac(1, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g0);
+            if (chain_end) gload(g0, ntiles * 4 + (t + 1 == ntiles ? 1 : 0));
+            float4 (&g_orph)[CG] = g1;
+            float4 (&g_end)[CG] = g0;
+#endif
             {
                 const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
                 const ulonglong2 c0 = chain_start ? zero : lds128_at<0>(orow);
                 const ulonglong2 c1 = chain_start ? zero : lds128_at<4096>(orow);
                 const ulonglong2 m0 = lds128_at<16 * 4>(trow), m1 = lds128_at<16 * 12>(trow);
-                pair_mac(0, lds128_at<0>(trow), c0, g0);
-                pair_mac(1, lds128_at<16 * 8>(trow), c1, g0);
+                pair_mac(0, lds128_at<0>(trow), c0, g_orph);
+                pair_mac(1, lds128_at<16 * 8>(trow), c1, g_orph);
                 if (chain_end) {
                     // the column left over at the end of a class is its own mirror: plain complex product with
                     // the entry (e.re, e.im) packed like a pair entry
@@ -403,7 +424,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                         const pk_t nxi = xi ^ 0x8000000080000000ull;
 #pragma unroll
                         for (int c = 0; c < CG; ++c) {
-                            const pk_t er = pk_make(g1[c].x, g1[c].y), ei = pk_make(g1[c].z, g1[c].w);
+                            const pk_t er = pk_make(g_end[c].x, g_end[c].y), ei = pk_make(g_end[c].z, g_end[c].w);
                             acc[0][c][b] = pk_fma(er, xr, acc[0][c][b]);
                             acc[0][c][b] = pk_fma(ei, nxi, acc[0][c][b]);
                             acc[1][c][b] = pk_fma(er, xi, acc[1][c][b]);
