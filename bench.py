@@ -53,10 +53,14 @@ def workload_name(seconds: float) -> str:
 # ------------------------------------------------------------------------------------------
 # synthetic capture: 5 FM carriers + AWGN, int16 interleaved
 # ------------------------------------------------------------------------------------------
-def synth_capture_device(n0: int, n: int, device, seed: int):
+def synth_capture_device(n0: int, n: int, device, seed: int, fs: float | None = None, carriers=None):
     """int16 [2*n] on `device` for global sample indices [n0, n0+n): carriers are functions of the
-    global index (float64 phase), noise is seeded per call."""
+    global index (float64 phase), noise is seeded per call.  `carriers`: (offset_hz, kind, tone_hz, amplitude) with
+    kind fm / am / usb / lsb; default: the five FM carriers of cfg2 at the module's FS."""
     import torch
+    fs = FS if fs is None else fs
+    if carriers is None:
+        carriers = [(off, "fm", 700.0 + 150.0 * i, 0.12) for i, off in enumerate(OFFSETS)]
     out = torch.empty(2 * n, dtype=torch.int16, device=device)
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -64,18 +68,147 @@ def synth_capture_device(n0: int, n: int, device, seed: int):
     two_pi = 2.0 * np.pi
     for s in range(0, n, step):
         m = min(step, n - s)
-        t = (torch.arange(m, device=device, dtype=torch.float64) + float(n0 + s)) / FS
+        t = (torch.arange(m, device=device, dtype=torch.float64) + float(n0 + s)) / fs
         re = torch.zeros(m, device=device, dtype=torch.float64)
         im = torch.zeros(m, device=device, dtype=torch.float64)
-        for i, off in enumerate(OFFSETS):
-            tone = 700.0 + 150.0 * i
-            ph = two_pi * off * t + (2500.0 / tone) * torch.sin(two_pi * tone * t)
+        for off, kind, tone, amp in carriers:
+            if kind == "fm":
+                ph, env = two_pi * off * t + (2500.0 / tone) * torch.sin(two_pi * tone * t), amp
+            elif kind == "am":
+                ph, env = two_pi * off * t, amp * (1.0 + 0.8 * torch.cos(two_pi * tone * t))
+            else:                                               # an analytic tone above (usb) / below (lsb) the carrier
+                ph, env = two_pi * (off + (tone if kind == "usb" else -tone)) * t, amp
             ph = torch.remainder(ph, two_pi)
-            re += 0.12 * torch.cos(ph)
-            im += 0.12 * torch.sin(ph)
+            re += env * torch.cos(ph)
+            im += env * torch.sin(ph)
         noise = torch.randn((m, 2), device=device, dtype=torch.float32, generator=gen) * 0.02
         iq = torch.stack((re.float() + noise[:, 0], im.float() + noise[:, 1]), dim=1).clamp_(-0.999, 0.999)
         out[2 * s:2 * (s + m)] = torch.round(iq * 32767.0).to(torch.int16).reshape(-1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE configurations, measured in the same run (the headline stays cfg2)
+# ------------------------------------------------------------------------------------------
+def other_workload_specs():
+    """(key, description, fs, seconds per GPU, [(offset, mode, bandwidth, agc)], all_ranks)"""
+    nfm = lambda offs: [(o, "nfm", 12_500.0, True) for o in offs]
+    grid = lambda c: [(-29.0 + 58.0 * (i + 0.5) / c) * 1e6 for i in range(c)]
+    return [
+        ("cfg1", "repo --benchmark shape: 2.5 MS/s, 5 s, 1 NFM target at +25 kHz", 2.5e6, 5.0, nfm([25e3]), False),
+        ("cfg3", "20 MS/s, AM + USB + LSB targets, AGC on (SSB on the bit-faithful path)", 20e6, 5.0,
+         [(2.3e6, "am", 10_000.0, True), (-4.1e6, "usb", 2_800.0, True), (6.2e6, "lsb", 2_800.0, True)], False),
+        ("cfg4", "61.44 MS/s, 5 NFM targets, one 10 s time shard per GPU (halo + recurrence warm-up), audio to "
+                 "per-target writers over NCCL", 61.44e6, 10.0, nfm([-21.3e6, -9.7e6, 1.9e6, 12.4e6, 25.1e6]), True),
+        ("cfg5_c16", "wideband sweep point: 61.44 MS/s, 16 NFM channels on a uniform grid", 61.44e6, 2.0, nfm(grid(16)), False),
+        ("cfg5_c256", "wideband sweep point: 61.44 MS/s, 256 NFM channels on a uniform grid", 61.44e6, 1.0, nfm(grid(256)), False),
+    ]
+
+
+def cpu_port_rate(fs: float, spec, n: int) -> float:
+    """Msamples/s of the oracle port on one host core for ONE target of the workload (bounded sample of n samples)."""
+    from oracle import iq_oracle as orc
+    off, mode, bw, agc = spec
+    kind = {"nfm": "fm", "am": "am", "usb": "usb", "lsb": "lsb"}[mode]
+    car = dict(offset=off, amp=0.2, kind=kind, tone=900.0)
+    if kind == "fm":
+        car["dev"] = 2500.0
+    if kind == "am":
+        car["depth"] = 0.8
+    x = orc.order_iq(orc.unpack_interleaved(orc.to_s16(orc.multi_carrier_capture(fs, n, [car], noise_std=0.02, seed=7)),
+                                            "pcm_s16le"), "iq")
+    plan = orc.TargetPlan(sample_rate=fs, freq_offset=off, bandwidth=bw, mode=mode, deemph_us=DEEMPH_US,
+                          agc_enabled=agc, filter_block=65_536, mix_sign=1)
+    from iq_to_audio_b200.processing import tune_chunk_size
+    t0 = time.perf_counter()
+    orc.run_target(x, plan, tune_chunk_size(fs, REQ_CHUNK))
+    return n / (time.perf_counter() - t0) / 1e6
+
+
+def run_other_workload(key, desc, fs, seconds, specs, dev, rank, world, peak, cpu: bool, reps: int = 3) -> dict:
+    """One BASELINE configuration resident in HBM through ChannelBank.process_resident_async; at world > 1 every
+    rank takes one time shard (sharding.plan_segments) and the audio goes to per-target writers after each pass."""
+    import torch
+    import torch.distributed as dist
+    from iq_to_audio_b200 import sharding
+    from iq_to_audio_b200.bank import ChannelBank, Target
+    from iq_to_audio_b200.processing import channel_decimation, design_channel_filter, tune_chunk_size
+    d, fs_ch = channel_decimation(fs, 96_000.0)
+    chunk = tune_chunk_size(fs, REQ_CHUNK)
+    n_seg = max(chunk, int(round(fs * seconds)) // chunk * chunk)
+    taps = {}
+    targets = []
+    for off, mode, bw, agc in specs:
+        if bw not in taps:
+            taps[bw] = design_channel_filter(fs, bw, d)
+        targets.append(Target(off, taps[bw], 1, mode, DEEMPH_US, agc))
+    bank = ChannelBank(fs, d, targets, codec="pcm_s16le", iq_order="iq", ref_chunk=chunk, device=dev.index)
+    seg = sharding.plan_segments(world * n_seg, world, chunk, d, bank.halo, targets, sample_rate=fs)[rank]
+    first = seg.first_frame
+    kinds = {"nfm": "fm", "am": "am", "usb": "usb", "lsb": "lsb"}
+    amp = min(0.12, 0.9 / max(1, len(specs)))
+    carriers = [(off, kinds[mode], 600.0 + 7.0 * i, amp) for i, (off, mode, bw, agc) in enumerate(specs)]
+    capture = synth_capture_device(first, seg.end - first + d, dev, 4321 + rank, fs, carriers)
+    rows = bank.rows_in(seg.begin, seg.end)
+    audio = torch.empty((bank.n_channels, rows), dtype=torch.float32, device=dev)
+    xchg = sharding.WriterExchange(bank.n_channels, rows, torch.float32, dev) if world > 1 else None
+    comp = torch.cuda.Stream(device=dev)
+
+    def step():
+        with torch.cuda.stream(comp):
+            bank.process_resident_async(capture.data_ptr(), first, seg.end - first + d, seg.begin, seg.end,
+                                        warmup_rows=seg.warmup_rows, dev_audio=audio.data_ptr(), out_stride=rows,
+                                        stream=comp.cuda_stream)
+            if xchg is not None:
+                for wk in xchg.exchange(0, audio, async_op=True):
+                    wk.wait()
+
+    def sync():
+        comp.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    sync()
+    bank.set_timing(True)
+    launches0 = bank.launches
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    comp.synchronize()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    timing = bank.get_timing()
+    launches = (bank.launches - launches0) // reps
+    bank.set_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_in = seg.end - max(0, seg.begin - seg.warmup_rows * d)
+    b_alg = 4.0 + len(specs) * 4.0 / d
+    chan_ms = timing["channelize_ms"] / max(timing["calls"], 1)
+    out = {"workload": desc, "samples_per_gpu": n_seg, "n_gpus": world, "ms": ms, "value": world * n_seg / (ms * 1e-3) / 1e6,
+           "unit": UNIT, "x_realtime": world * n_seg / fs / (ms * 1e-3), "decimation": d, "taps": sorted({len(t) for t in taps.values()}),
+           "fft_size": bank.fft_size, "kernel_generation": bank.kernel_generation, "channels": len(specs),
+           "channelize_ms": chan_ms, "tail_ms": timing["tail_ms"] / max(timing["calls"], 1), "gpu_launches": launches,
+           "roofline": {"algorithmic_bytes_per_sample": b_alg, "achieved": n_in * b_alg / (chan_ms * 1e-3) / 1e9 if chan_ms > 0 else None,
+                        "step_achieved": n_seg * b_alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": n_in * b_alg / (chan_ms * 1e-3) / 1e9 / peak if chan_ms > 0 else None,
+                        "step_frac": n_seg * b_alg / (ms * 1e-3) / 1e9 / peak}}
+    bank.close()
+    del capture, audio
+    torch.cuda.empty_cache()
+    if cpu and rank == 0:
+        n_cpu = 1 << 21
+        per_target = float(np.mean([cpu_port_rate(fs, sp, n_cpu) for sp in specs[:3:2] or specs[:1]]))
+        out["cpu_port"] = {"value": per_target / len(specs), "unit": UNIT, "cores": 1, "kind": "port",
+                           "per_target": per_target,
+                           "sample": f"{n_cpu} samples per target, one target of each filter length timed, targets sequential as cli.py:683 runs them"}
+        out["speedup_vs_cpu_port_1core"] = out["value"] / out["cpu_port"]["value"]
     return out
 
 
@@ -210,6 +343,7 @@ def main() -> None:
     ap.add_argument("--seconds", type=float, default=SECONDS, help="capture length per GPU (default 60 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (cfg1, cfg3, cfg4, cfg5 points)")
     ap.add_argument("--peer-gather", action="store_true",
                     help="multi-GPU: push the audio into rank 0's memory with copy engines (sharding.PeerGather) "
                          "instead of the NCCL gather")
@@ -499,18 +633,36 @@ def main() -> None:
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e2e_ms,
                "api": "ChannelBank.stream: submit/collect per 4 Mi-sample reference chunk, 2 in flight, pinned host input"}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (k_channelize) ---------------------------------------
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
         peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- the other BASELINE configurations (cfg1, cfg3, cfg4 time-sharded over all ranks, two cfg5 points) ----
+    others = None
+    if not args.no_others:
+        del capture
+        torch.cuda.empty_cache()
+        others = {}
+        for key, desc, fs_w, secs, specs, all_ranks in other_workload_specs():
+            if not all_ranks and rank != 0:
+                continue
+            try:
+                others[key] = run_other_workload(key, desc, fs_w, secs, specs, dev, rank if all_ranks else 0,
+                                                 world if all_ranks else 1, peak, cpu=not args.no_cpu_baseline)
+            except Exception as exc:                       # a failed extra must not take the headline number with it
+                others[key] = {"workload": desc, "error": repr(exc)[:300]}
+        if world > 1:
+            dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_channelize) ---------------------------------------
     n_in = seg_end - max(0, seg_begin - warm_rows * d)                 # samples one launch turns into channel rows
     b_alg = 4.0 + sum(4.0 / d for _ in OFFSETS)                        # int16 in once + f32 audio out
     chan_ms = timing["channelize_ms"] / max(timing["calls"], 1)
@@ -560,7 +712,7 @@ def main() -> None:
                    "gather_verified": gather_ok,
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "other_workloads": others,
         "clocks": clocks.summary(),
     }
     _emit(line)

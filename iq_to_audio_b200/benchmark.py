@@ -54,17 +54,20 @@ def write_synthetic_capture(path: Path, sample_rate: float, seconds: float, freq
     if count <= 0:
         raise ValueError("Benchmark duration is too short to generate samples.")
     noise = np.random.default_rng(42).normal(scale=noise_std, size=(count, 2))     # one draw for the whole capture
-    step = 2.0 * math.pi * freq_offset / sample_rate
     with wave.open(str(path), "wb") as wav:
         wav.setparams((2, 2, int(sample_rate), 0, "NONE", "not compressed"))
         for lo in range(0, count, _WAV_BLOCK):
             hi = min(count, lo + _WAV_BLOCK)
-            phase = step * np.arange(lo, hi, dtype=np.float64)
-            frame = noise[lo:hi].copy()
-            frame[:, 0] += amplitude * np.cos(phase)
-            frame[:, 1] += amplitude * np.sin(phase)
-            pcm = np.round(np.clip(frame.astype(np.float32), -0.999, 0.999) * 32767.0)
-            wav.writeframes(pcm.astype("<i2").tobytes())
+            # every float64 operation in the reference's order (benchmark.py:31-37): t = n / fs, the phase as
+            # ((2 pi) * offset) * t, the tone through the complex exponential -- a phase formed as
+            # (2 pi offset / fs) * n differs in the last bits at n ~ 1e7 and flips a few int16 roundings
+            t = np.arange(lo, hi, dtype=np.float64) / sample_rate
+            tone = np.exp(1j * 2.0 * math.pi * freq_offset * t)
+            i = amplitude * tone.real + noise[lo:hi, 0]
+            q = amplitude * tone.imag + noise[lo:hi, 1]
+            frame = np.clip(np.column_stack((i, q)).astype(np.float32), -0.999, 0.999)
+            # libsndfile's float -> PCM_16 (pcm.c f2s_array): lrintf(x * 32767.0f), float32 arithmetic
+            wav.writeframes(np.rint(frame * np.float32(32767.0)).astype("<i2").tobytes())
     return count
 
 

@@ -95,6 +95,9 @@ struct Group {
     int first, count;
     size_t g_off;     // offset (float2 elements) into d_gtab
     size_t g5_off;    // offset (float4 elements) into d_gtab5
+    PairGeo pair;     // generation 5 geometry of this group's filter length
+    bool pair_ok;     // symmetric taps of one length: the mirror-pair kernel takes the group
+    bool skip;        // every channel of the group is on the bit-faithful path (precise.cu computes its samples)
 };
 
 }  // namespace iq2a
@@ -127,8 +130,7 @@ struct iq2a_bank {
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     int* d_setctr = nullptr;        // block-set counter of the generation-5 kernel (dynamic scheduling)
     float4* d_gtab5 = nullptr;      // mirror-pair table of the generation-5 kernel (channelizer5.cuh)
-    PairGeo pair{};
-    bool pair_ok = false;
+    bool pair_ok = false;           // at least one group on the mirror-pair kernel
     bool v2_ok = false;
     bool cp_ok = false;             // generation 4 with cp.async staging is available (int16, M = 512, any D)
     int kernel_gen = 1;             // 3: warp-specialised kernel, 2: TMA + packed transforms, 1: first generation
@@ -275,6 +277,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     if (use_cp) mg_split = a.mg_end;
     else if (!use_v2) mg_split = a.mg_begin;
     for (const Group& g : b->groups) {
+        if (g.skip) continue;                        // bit-faithful channels only: precise.cu below computes them
         ChannelizeParams p{};
         p.raw = a.d_raw;
         p.raw_n0 = a.raw_n0;
@@ -299,14 +302,14 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
             p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
             p.gtab = b->d_gtab2 + g.g_off;
             p.out = b->d_bb + (size_t)g.first * stride;
-            if (use_v2 && b->pair_ok) {
+            if (use_v2 && g.pair_ok) {
                 // kappa^{1/2} = e^{-j w (L-1)/2} of the pair identity joins the output rotation
                 const double half_len = 0.5 * (double)(b->taps[g.first].size() - 1);
                 for (int i = 0; i < g.count; ++i) p.phase_bias[i] = py_fmod(-b->w[g.first + i] * half_len, 2.0 * M_PI);
                 p.gtab = reinterpret_cast<const float2*>(b->d_gtab5 + g.g5_off);
                 p.set_counter = b->d_setctr;
                 IQ2A_CUDA_TRY(cudaMemsetAsync(b->d_setctr, 0, sizeof(int), a.st));
-                rc = launch_channelize5(p, g.count, b->pair, t_base, t_row0, t_rows, b->n_sm, a.st);
+                rc = launch_channelize5(p, g.count, g.pair, t_base, t_row0, t_rows, b->n_sm, a.st);
             } else if (use_v2) rc = launch_channelize2(p, g.count, t_base, t_row0, t_rows, b->n_sm, a.st);
             else rc = launch_channelize2_cp(p, g.count, b->n_sm, a.st);
             if (rc) return rc;
@@ -540,10 +543,14 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     const int vd = (nt_max - 1 + D - 1) / D + 1;      // plan.py: overlap_rows
     int M = cfg->fft_size;
     if (M == 0) {
-        // cost per new sample ~ (5 log2 M + 8 C') / (1 - vd/M); 1024 only when it clearly wins
+        // cost per new sample ~ (5 log2 M + 8 C') / (1 - vd/M); 1024 only when it clearly wins -- and never for int16
+        // input whose filter fits 512: the TMA / packed-f32x2 kernels (generations 4, 5) exist for M = 512 only and
+        // are 2-3x faster than the first-generation kernel that would take M = 1024
         const double cm = std::min(cfg->n_channels, 6);
         auto cost = [&](int m) { return m <= vd + 16 ? 1e300 : (5.0 * std::log2((double)m) + 8.0 * cm) / (1.0 - (double)vd / m); };
         M = (cost(1024) < 0.95 * cost(512)) ? 1024 : 512;
+        const char* env = std::getenv("IQ2A_CHANNELIZER");
+        if (cfg->codec == IQ2A_CODEC_S16 && vd + 16 < 512 && !(env && std::strcmp(env, "v1") == 0)) M = 512;
         if (cost(M) >= 1e300) { set_error("channel filter too long for the supported transform sizes (%d history rows)", vd); return IQ2A_ERR_INVALID; }
     }
     if (M != 512 && M != 1024) { set_error("fft_size must be 512 or 1024"); return IQ2A_ERR_INVALID; }
@@ -607,15 +614,33 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         tn[c] = ch[c].ntaps;
         all_taps.insert(all_taps.end(), b->taps[c].begin(), b->taps[c].end());
     }
-    // channel groups
+    // channel groups: runs of consecutive channels with the same filter length on the same path (fast / bit-faithful),
+    // each run in groups of <= gmax channels -- so that a group can take the mirror-pair kernel with its own geometry
+    // and a group of bit-faithful channels is not computed twice; too many runs: plain groups of consecutive channels
     const int gmax = channelize_max_group(M);
-    const int ng = (C + gmax - 1) / gmax;
     size_t g_total = 0;
-    for (int g = 0, first = 0; g < ng; ++g) {
-        const int count = C / ng + (g < C % ng ? 1 : 0);
-        b->groups.push_back(Group{first, count, g_total, 0});
-        g_total += (size_t)D * count * M;
-        first += count;
+    {
+        std::vector<std::pair<int, int>> runs;                 // (first, count)
+        for (int c = 0; c < C; ++c) {
+            if (!runs.empty() && tn[c] == tn[c - 1] && tc[c].precise == tc[c - 1].precise) runs.back().second++;
+            else runs.push_back({c, 1});
+        }
+        if ((int)runs.size() > 8) runs.assign(1, {0, C});
+        for (const auto& run : runs) {
+            const int ng = (run.second + gmax - 1) / gmax;
+            for (int g = 0, first = run.first; g < ng; ++g) {
+                const int count = run.second / ng + (g < run.second % ng ? 1 : 0);
+                Group grp{};
+                grp.first = first;
+                grp.count = count;
+                grp.g_off = g_total;
+                grp.skip = true;
+                for (int i = 0; i < count; ++i) grp.skip = grp.skip && tc[first + i].precise;
+                b->groups.push_back(grp);
+                g_total += (size_t)D * count * M;
+                first += count;
+            }
+        }
     }
     // device tables
     std::vector<double2> wtab(M);
@@ -680,25 +705,27 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         const char* stg = std::getenv("IQ2A_STAGING");               // "cp": cp.async staging even where TMA applies
         b->v2_ok = bulk && D % 4 == 0 && channelize2_available() && !(stg && std::strcmp(stg, "cp") == 0);
         b->cp_ok = bulk;
-        // generation 5 (mirror pairs): every channel the same number of taps, each filter exactly symmetric
+        // generation 5 (mirror pairs), per group: every channel the same number of taps, each filter exactly symmetric
         // (firwin's are, processing.py:613-619), and a rotation that fits the staging geometry
-        bool sym = b->v2_ok && !force_v4;
-        for (int c = 0; c < C && sym; ++c) {
-            sym = tn[c] == tn[0];
-            const std::vector<double>& h = b->taps[c];
-            for (size_t i = 0, n = h.size(); i < n / 2 && sym; ++i) sym = h[i] == h[n - 1 - i];
+        size_t g5_total = 0;
+        for (Group& g : b->groups) {
+            bool sym = b->v2_ok && !force_v4 && !g.skip;
+            for (int i = 0; i < g.count && sym; ++i) {
+                const int c = g.first + i;
+                sym = tn[c] == tn[g.first];
+                const std::vector<double>& h = b->taps[c];
+                for (size_t k = 0, n = h.size(); k < n / 2 && sym; ++k) sym = h[k] == h[n - 1 - k];
+            }
+            g.pair_ok = sym && pair_geometry(tn[g.first], D, &g.pair);
+            if (g.pair_ok) {
+                g.g5_off = g5_total;
+                g5_total += (size_t)pair_table_entries(g.pair) * g.count * 256;
+                b->pair_ok = true;
+            }
         }
-        b->pair_ok = sym && pair_geometry(tn[0], D, &b->pair);
         b->kernel_gen = b->pair_ok ? 5 : ((b->v2_ok || b->cp_ok) ? 4 : 1);
         if ((b->v2_ok || b->cp_ok) && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
-        if (b->pair_ok) {
-            size_t g5_total = 0;
-            for (Group& g : b->groups) {
-                g.g5_off = g5_total;
-                g5_total += (size_t)pair_table_entries(b->pair) * g.count * 256;
-            }
-            if ((rc = dev_alloc(&b->d_gtab5, g5_total)) || (rc = dev_alloc(&b->d_setctr, (size_t)1))) { cudaFree(d_wtab); return fail(rc); }
-        }
+        if (b->pair_ok && ((rc = dev_alloc(&b->d_gtab5, g5_total)) || (rc = dev_alloc(&b->d_setctr, (size_t)1)))) { cudaFree(d_wtab); return fail(rc); }
     }
     for (const Group& g : b->groups)
         for (int i = 0; i < g.count; ++i) {
@@ -708,11 +735,11 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             if (!rc && (b->v2_ok || b->cp_ok))
                 rc = launch_build_g(b->d_taps + toff[c], tn[c], b->w[c], D, M, b->R1, vd, d_wtab,
                                     b->d_gtab2 + g.g_off, g.count, i, 2, 1.0 / 32768.0, b->stream);
-            if (!rc && b->pair_ok)
+            if (!rc && g.pair_ok)
                 rc = launch_build_gpair(b->d_taps + toff[c], tn[c], b->w[c], D, vd, d_wtab, b->d_gtab5 + g.g5_off,
-                                        g.count, i, 1.0 / 32768.0, b->pair, b->stream);
+                                        g.count, i, 1.0 / 32768.0, g.pair, b->stream);
             if (rc) { cudaFree(d_wtab); return fail(rc); }
-            b->launches += 1 + ((b->v2_ok || b->cp_ok) ? 1 : 0) + (b->pair_ok ? 1 : 0);
+            b->launches += 1 + ((b->v2_ok || b->cp_ok) ? 1 : 0) + (g.pair_ok ? 1 : 0);
         }
     b->tap_off = toff;
     if ((rc = dev_alloc(&b->d_rot, (size_t)C * b->ld)) || (rc = launch_build_rot(b->d_w, C, D, b->ld, b->d_rot, b->stream))) {

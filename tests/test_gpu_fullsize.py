@@ -65,7 +65,8 @@ def test_cfg2_full_size_shards_and_oracle_windows():
         # ---- oracle windows ----
         taps = np.asarray(targets[0].taps, dtype=np.float64)
         win = 600_000                                                 # input samples handed to the oracle per window
-        for k0, ci in ((0, 1), (124, 3)):                             # chunk 124 starts at 5.2e8 samples (52 s)
+        # all five targets, each at the stream start and across a chunk boundary 52 s in (chunk 124 = 5.2e8 samples)
+        for k0, ci in [(k, c) for k in (0, 124) for c in range(len(targets))]:
             s0 = k0 * chunk
             lo = s0 if k0 else 0
             if k0:

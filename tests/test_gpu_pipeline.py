@@ -205,3 +205,42 @@ def test_pass_through_raw_containers(tmp_path, suffix, codec):
     else:
         assert np.max(np.abs(data.astype(np.float64) - bb)) < 2e-6
     assert abs(r.audio_peak - float(np.max(np.abs(bb.view(np.complex128))))) < 1e-5
+
+
+def test_benchmark_run_matches_the_unmodified_reference_pipeline(tmp_path, no_ffmpeg, monkeypatch):
+    """Whole-pipeline surface at the repo's own --benchmark configuration (2.5 MS/s, 5 s, NFM at +25 kHz, chunk
+    1 Mi, filter block 65 536, mix sign probed on the warm-up chunk): the float32 stream the product pipeline hands
+    to its encoder against the stream the UNMODIFIED reference handed to ffmpeg (tests/golden/pipeline_cfg1.npz,
+    make_pipeline_golden.py), <= 1e-4; the 48 kHz PCM_16 file against libswresample's arithmetic on the reference's
+    stream, +-1 LSB; the running peak to 1e-5."""
+    import hashlib
+    from pathlib import Path
+    from iq_to_audio_b200 import pipeline as gp
+    from iq_to_audio_b200.benchmark import write_synthetic_capture
+
+    g = np.load(Path(__file__).parent / "golden" / "pipeline_cfg1.npz")
+    cap = tmp_path / "benchmark_fc-400000000Hz.wav"
+    n = write_synthetic_capture(cap, float(g["sample_rate"]), float(g["seconds"]), float(g["freq_offset"]))
+    blob = cap.read_bytes()
+    assert n == int(g["capture_frames"])
+    assert hashlib.sha256(blob[blob.index(b"data") + 8:]).hexdigest() == str(g["capture_sha256"])   # same input
+    parts = []
+    real = gp.AudioWriter.write_clipped
+
+    def spy(self, safe):
+        parts.append(np.array(safe, dtype=np.float32, copy=True))
+        return real(self, safe)
+
+    monkeypatch.setattr(gp.AudioWriter, "write_clipped", spy)
+    cfg = gp.ProcessingConfig(in_path=cap, target_freq=400_025_000.0, center_freq=400_000_000.0,
+                              center_freq_source="benchmark", demod_mode="nfm", output_path=tmp_path / "audio.wav")
+    r = gp.ProcessingPipeline(cfg).run()
+    stream = np.concatenate(parts)
+    want = g["clipped"]
+    assert r.decimation == 26 and r.mix_sign == 1 and stream.size == want.size == 480_770
+    assert np.abs(stream - want).max() <= 1e-4                    # measured ~3e-8
+    assert abs(r.audio_peak - float(np.abs(want).max())) <= 1e-5  # nothing clips in this run: peak == max |stream|
+    rate, pcm = _read_pcm(r.output_path)
+    ref_pcm = SwrModel(int(g["ffmpeg_rate"])).resample_s16(want)
+    assert rate == 48_000 and pcm.size == ref_pcm.size
+    assert np.abs(pcm.astype(np.int64) - ref_pcm.astype(np.int64)).max() <= 1

@@ -180,3 +180,28 @@ def test_unpack_rules_and_ragged_tail():
     with pytest.raises(ValueError):
         orc.order_iq(il, "xy")
     assert orc.unpack_interleaved(b"", "pcm_s16le").size == 0
+
+
+def test_oracle_reproduces_the_reference_pipeline_run_bit_for_bit(tmp_path):
+    """`tests/golden/pipeline_cfg1.npz` holds the float32 stream the UNMODIFIED reference handed to its encoder in a
+    `run_benchmark -> ProcessingPipeline.run` run of the repo's own --benchmark configuration (2.5 MS/s, 5 s, NFM at
+    +25 kHz, chunk 1 Mi, filter block 65 536, mix sign probed) -- `make_pipeline_golden.py` ran it with a stub
+    soundfile and a shim ffmpeg.  The oracle's replay of the loop on the same capture must give the same bytes, and the
+    capture written by the product's own `--benchmark` generator must be the capture the reference generated."""
+    import hashlib
+    from pathlib import Path
+    from iq_to_audio_b200.benchmark import write_synthetic_capture
+
+    g = np.load(Path(__file__).parent / "golden" / "pipeline_cfg1.npz")
+    cap = tmp_path / "benchmark_fc-400000000Hz.wav"
+    n = write_synthetic_capture(cap, float(g["sample_rate"]), float(g["seconds"]), float(g["freq_offset"]))
+    blob = cap.read_bytes()
+    pos = blob.index(b"data") + 8
+    assert n == int(g["capture_frames"]) and hashlib.sha256(blob[pos:]).hexdigest() == str(g["capture_sha256"])
+    raw = np.frombuffer(blob[pos:], dtype="<i2")
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    plan = orc.TargetPlan(sample_rate=float(g["sample_rate"]), freq_offset=float(g["freq_offset"]), mix_sign=None)
+    res = orc.run_target(x, plan, orc.plan_chunk(float(g["sample_rate"]), 1_048_576))
+    assert int(g["ffmpeg_rate"]) == int(round(plan.fs_channel)) == 96_154
+    assert res.clipped.dtype == np.float32 and res.clipped.size == g["clipped"].size
+    assert np.array_equal(res.clipped, g["clipped"])
