@@ -403,6 +403,10 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the streaming (e2e) leg is bound by host->device copies: keep this rank's threads and the pinned buffers it
+    # allocates from here on next to the GPU's PCIe root
+    from iq_to_audio_b200.numa import bind_to_device_numa
+    placement = bind_to_device_numa(local_rank)
     if world > 1:
         # keep stdout to the single JSON line: NCCL's version/info banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -596,10 +600,15 @@ def main() -> None:
     launches = bank.launches - launches0
     bank.set_timing(False)
     sync_all()
+    per_rank = None
     if world > 1:
-        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+        mine = torch.tensor([step_ms, timing["channelize_ms"] / max(timing["calls"], 1), float(placement.get("numa_node") if placement.get("numa_node") is not None else -1)],
+                            dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"step_ms": [round(float(v[0]), 4) for v in every], "kernel_ms": [round(float(v[1]), 4) for v in every],
+                    "numa_node": [int(v[2]) for v in every]}
+        step_ms = max(per_rank["step_ms"])
 
     # ---- e2e: pinned host capture streamed through process_chunk -----------------------------
     e2e = None
@@ -610,12 +619,15 @@ def main() -> None:
         nchunks = (n_seg + chunk - 1) // chunk
         bytes_out = 0
 
+        batch = max(1, min(8, -(-49_152 * d // chunk)))          # reference chunks per GPU call (pipeline.py's rule)
+
         def e2e_step():
             nonlocal bytes_out
             bank.reset()
             bytes_out = 0
-            views = (host_np[2 * k * chunk:2 * min((k + 1) * chunk, n_seg)] for k in range(nchunks))
-            for r in bank.stream(views):
+            span = batch * chunk
+            views = (host_np[2 * s:2 * min(s + span, n_seg)] for s in range(0, n_seg, span))
+            for r in bank.stream(views, chunk_frames=chunk):
                 bytes_out += r.audio.nbytes + r.clipped.nbytes
         e2e_step()
         sync_all()
@@ -625,13 +637,17 @@ def main() -> None:
             e2e_step()
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+        e2e_rank_ms = [e2e_ms]
         if world > 1:
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            e2e_rank_ms = [float(v.item()) for v in every]
+            e2e_ms = max(e2e_rank_ms)
         e2e = {"value": world * n_seg / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(4 * n_seg),
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e2e_ms,
-               "api": "ChannelBank.stream: submit/collect per 4 Mi-sample reference chunk, 2 in flight, pinned host input"}
+               "per_rank_h2d_GBps": [round(4 * n_seg / (m * 1e-3) / 1e9, 2) for m in e2e_rank_ms],
+               "api": f"ChannelBank.stream(chunk_frames={chunk}): submit/collect of {batch} reference chunks per call, 2 calls in flight, pinned host input"}
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -713,6 +729,7 @@ def main() -> None:
                    "l2": f"input {4 * n_seg / 1e9:.2f} GB per GPU >> 126 MB L2, read once per step"},
         "x_realtime": value * 1e6 / FS,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "other_workloads": others,
+        "per_rank": per_rank, "host_placement": placement,
         "clocks": clocks.summary(),
     }
     _emit(line)

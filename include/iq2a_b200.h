@@ -140,6 +140,19 @@ int iq2a_bank_submit_chunk(iq2a_bank* bank, const void* frames, int64_t n_frames
 int iq2a_bank_collect_chunk(iq2a_bank* bank, float* audio, float* clipped, float* baseband,
                             int64_t out_stride, int64_t* n_out, double* rms_dbfs);
 
+/* Several iterations of the reference loop body (processing.py:1070-1154) in ONE call: `frames` holds
+ * ceil(n_frames / chunk_frames) consecutive reference chunks of chunk_frames frames (the last may be shorter).
+ * The NCO phase wraps (:295), the SSB AGC restarts (decoders/ssb.py:67) and DecoderStats are taken per reference
+ * chunk exactly as if each had been submitted on its own -- only the kernels see them together, which is what fills
+ * the GPU at high decimation (one 4 Mi-sample chunk of a 61.44 MS/s capture is 7 block sets for 296 CTA slots).
+ * chunk_frames == 0: the call is one reference chunk (iq2a_bank_submit_chunk).
+ * collect: rms_dbfs [C][rms_capacity] and window_rows [rms_capacity] receive one entry per reference chunk of the
+ * call (window_rows = the Decimator.process output size of that chunk), n_windows their number. */
+int iq2a_bank_submit_chunks(iq2a_bank* bank, const void* frames, int64_t n_frames, int64_t chunk_frames, int32_t want);
+int iq2a_bank_collect_chunks(iq2a_bank* bank, float* audio, float* clipped, float* baseband, int64_t out_stride,
+                             int64_t* n_out, double* rms_dbfs, int64_t rms_capacity, int64_t* window_rows,
+                             int64_t* n_windows);
+
 /*
  * Whole-segment step on data already resident in HBM (bench / time-sharded runs).
  * `dev_frames` holds global sample indices [first_frame, first_frame + n_frames).

@@ -26,7 +26,7 @@ SYMBOLS = (
     "iq2a_last_error", "iq2a_version", "iq2a_device_count", "iq2a_host_alloc", "iq2a_host_free",
     "iq2a_bank_create", "iq2a_bank_destroy", "iq2a_bank_info_get", "iq2a_bank_reset",
     "iq2a_bank_get_state", "iq2a_bank_set_state", "iq2a_bank_process_chunk",
-    "iq2a_bank_submit_chunk", "iq2a_bank_collect_chunk",
+    "iq2a_bank_submit_chunk", "iq2a_bank_collect_chunk", "iq2a_bank_submit_chunks", "iq2a_bank_collect_chunks",
     "iq2a_bank_process_resident", "iq2a_bank_process_resident_async", "iq2a_bank_launch_count",
     "iq2a_bank_copy_gtable", "iq2a_bank_set_timing", "iq2a_bank_get_timing", "iq2a_bank_set_sm_reserve",
     "iq2a_unpack_mix", "iq2a_fir", "iq2a_decimate", "iq2a_demod", "iq2a_scan",
@@ -94,6 +94,9 @@ def load() -> C.CDLL:
     lib.iq2a_bank_process_chunk.argtypes = [vp, vp, i64, fp, fp, fp, i64, C.POINTER(i64), C.POINTER(f64)]
     lib.iq2a_bank_submit_chunk.argtypes = [vp, vp, i64, i32]
     lib.iq2a_bank_collect_chunk.argtypes = [vp, fp, fp, fp, i64, C.POINTER(i64), C.POINTER(f64)]
+    lib.iq2a_bank_submit_chunks.argtypes = [vp, vp, i64, i64, i32]
+    lib.iq2a_bank_collect_chunks.argtypes = [vp, fp, fp, fp, i64, C.POINTER(i64), C.POINTER(f64), i64, C.POINTER(i64),
+                                             C.POINTER(i64)]
     lib.iq2a_bank_process_resident.argtypes = [vp, vp, i64, i64, i64, i64, i32, fp, fp, fp, i64,
                                                C.POINTER(i64), C.POINTER(f64), i64]
     lib.iq2a_bank_process_resident_async.argtypes = [vp, vp, i64, i64, i64, i64, i32, fp, fp, fp, i64, vp]

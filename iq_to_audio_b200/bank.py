@@ -32,8 +32,9 @@ class ChunkResult:
     audio: np.ndarray                  # float32 [C, n] decoder output (pre-clip)
     clipped: np.ndarray                # float32 [C, n] what the writer pipes to the encoder
     baseband: np.ndarray | None        # complex64 [C, n] decimated channel samples (if requested)
-    rms_dbfs: np.ndarray               # float64 [C]
+    rms_dbfs: np.ndarray               # float64 [C] (one reference chunk per call) or [C, W] (stream(..., chunk_frames=))
     count: int                         # n
+    window_counts: np.ndarray | None = None   # int64 [W]: rows of every reference chunk the call covered
 
 
 class ChannelBank:
@@ -180,12 +181,19 @@ class ChannelBank:
         k = int(n_out.value)
         return ChunkResult(audio[:, :k], clipped[:, :k], None if bb is None else bb[:, :k], rms, k)
 
-    def stream(self, chunks, *, want_baseband: bool = False, want_audio: bool = True, want_clipped: bool = True):
+    def stream(self, chunks, *, want_baseband: bool = False, want_audio: bool = True, want_clipped: bool = True,
+               chunk_frames: int | None = None):
         """Pipelined form of `process_chunk` over an iterable of raw PCM chunks: chunk k+1 is
         submitted (H2D copy queued) before chunk k's results are collected, so the copy of the next
-        chunk overlaps the kernels of the current one.  Yields one `ChunkResult` per chunk, in order."""
+        chunk overlaps the kernels of the current one.  Yields one `ChunkResult` per chunk, in order.
+
+        `chunk_frames`: every item of `chunks` may hold SEVERAL consecutive reference chunks of that many frames
+        (the last one shorter); phase wraps, AGC restarts and statistics stay per reference chunk
+        (iq2a_bank_submit_chunks) while the kernels see the whole item -- at high decimation one reference chunk
+        is too few rows to fill the GPU.  `rms_dbfs` is then [C, W] and `window_counts` [W]."""
         want = (1 if want_audio else 0) | (2 if want_clipped else 0) | (4 if want_baseband else 0)
         pending = []          # [(keepalive, n_frames)]
+        cf = int(chunk_frames) if chunk_frames else 0
 
         def collect(n):
             cap = max(1, (n + self.decimation - 1) // self.decimation + 1)
@@ -193,18 +201,23 @@ class ChannelBank:
             audio = np.empty((cc, cap), dtype=np.float32) if want_audio else None
             clipped = np.empty((cc, cap), dtype=np.float32) if want_clipped else None
             bb = np.empty((cc, cap), dtype=np.complex64) if want_baseband else None
-            rms = np.zeros(cc, dtype=np.float64)
-            n_out = C.c_int64(0)
-            _lib.check(self._lib.iq2a_bank_collect_chunk(self._h, _lib.ptr(audio), _lib.ptr(clipped), _lib.ptr(bb), cap,
-                                                         C.byref(n_out), rms.ctypes.data_as(C.POINTER(C.c_double))))
-            k = int(n_out.value)
+            wcap = max(1, (n + cf - 1) // cf) if cf else 1
+            rms = np.zeros((cc, wcap), dtype=np.float64)
+            wrows = np.zeros(wcap, dtype=np.int64)
+            n_out, n_win = C.c_int64(0), C.c_int64(0)
+            _lib.check(self._lib.iq2a_bank_collect_chunks(
+                self._h, _lib.ptr(audio), _lib.ptr(clipped), _lib.ptr(bb), cap, C.byref(n_out),
+                rms.ctypes.data_as(C.POINTER(C.c_double)), wcap, wrows.ctypes.data_as(C.POINTER(C.c_int64)),
+                C.byref(n_win)))
+            k, w = int(n_out.value), int(n_win.value)
             return ChunkResult(None if audio is None else audio[:, :k], None if clipped is None else clipped[:, :k],
-                               None if bb is None else bb[:, :k], rms, k)
+                               None if bb is None else bb[:, :k], rms[:, :w] if cf else rms[:, 0], k,
+                               wrows[:w] if cf else None)
 
         for raw in chunks:
             addr, n = self.frames_in(raw)
             keep = self._keep
-            _lib.check(self._lib.iq2a_bank_submit_chunk(self._h, addr, n, want))
+            _lib.check(self._lib.iq2a_bank_submit_chunks(self._h, addr, n, cf, want))
             pending.append((keep, n))
             if len(pending) == 2:
                 _, n0 = pending.pop(0)

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <new>
 #include <vector>
 
@@ -60,6 +61,8 @@ static int dev_grow(T** p, size_t* cap, size_t need) {
 // results of one streamed chunk, in pinned host memory
 struct StreamSlot {
     int64_t rows = 0, n_frames = 0;
+    int64_t n0 = 0, chunk_frames = 0;   // first input sample and reference-chunk length of the call
+    int nwin = 1;                       // reference chunks (statistics windows) in the call
     int want = 0;
     cudaEvent_t copied = nullptr, done = nullptr;
     bool done_valid = false;
@@ -68,8 +71,9 @@ struct StreamSlot {
     float2* h_bb = nullptr;
     double* h_ss = nullptr;
     size_t cap = 0;
+    size_t ss_cap = 0;
     int ensure(size_t nfl, int C) {
-        if (nfl <= cap && h_ss) return 0;
+        if (nfl <= cap && h_ss && (size_t)C <= ss_cap) return 0;
         release();
         const size_t want_n = nfl + nfl / 4 + 1024;
         if (cudaHostAlloc((void**)&h_audio, want_n * sizeof(float), cudaHostAllocDefault) != cudaSuccess ||
@@ -80,6 +84,7 @@ struct StreamSlot {
             return -4;
         }
         cap = want_n;
+        ss_cap = (size_t)C;
         return 0;
     }
     void release() {
@@ -87,7 +92,7 @@ struct StreamSlot {
         if (h_clip) cudaFreeHost(h_clip);
         if (h_bb) cudaFreeHost(h_bb);
         if (h_ss) cudaFreeHost(h_ss);
-        h_audio = h_clip = nullptr; h_bb = nullptr; h_ss = nullptr; cap = 0;
+        h_audio = h_clip = nullptr; h_bb = nullptr; h_ss = nullptr; cap = 0; ss_cap = 0;
     }
 };
 
@@ -115,6 +120,9 @@ struct iq2a_bank {
     std::vector<double> w;          // signed NCO increments (sign * -2 pi f_off / fs)
     std::vector<double> phase;      // streaming: NCO phase at n_pos per channel
     std::vector<std::vector<double>> phase_tab;   // resident: per-chunk start phases (grown lazily)
+    // streaming: start sample and per-channel start phase of the most recent reference chunks (oldest first), for the
+    // bit-faithful mixer's view of the filter history (precise.cuh: MixExactParams::hist_*)
+    std::deque<std::pair<int64_t, std::vector<double>>> phase_hist;
     std::vector<Group> groups;
     int64_t n_pos = 0;              // streaming: input samples consumed
     int64_t launches = 0;
@@ -217,6 +225,7 @@ struct CoreArgs {
     int64_t raw_pad;                     // frames readable (finite garbage allowed) beyond raw_len
     int64_t mg_begin, mg_emit, mg_end;   // rows [mg_begin, mg_end) computed, [mg_emit, mg_end) emitted
     bool fresh;
+    bool use_hist;                       // streaming call: earlier calls' reference chunks in bank->phase_hist
     // phase / segmentation model
     int64_t seg_origin, seg_len;
     int nseg;
@@ -375,6 +384,17 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
                 m.phase.nseg = a.nseg;
                 m.chan = c;
                 m.w = b->w[c];
+                m.nhist = 0;
+                if (a.use_hist) {
+                    // the newest kMixHist reference chunks that started before this call
+                    size_t n_prev = 0;
+                    while (n_prev < b->phase_hist.size() && b->phase_hist[n_prev].first < a.seg_origin) ++n_prev;
+                    for (size_t i = n_prev > (size_t)kMixHist ? n_prev - kMixHist : 0; i < n_prev; ++i) {
+                        m.hist_start[m.nhist] = b->phase_hist[i].first;
+                        m.hist_phase[m.nhist] = b->phase_hist[i].second[c];
+                        ++m.nhist;
+                    }
+                }
                 if ((rc = dev_grow(&b->d_mixed, &b->mixed_cap, (size_t)m.count))) return rc;
                 m.mixed = b->d_mixed;
                 if ((rc = launch_mix_exact(m, b->cfg.codec, a.st))) return rc;
@@ -781,6 +801,7 @@ int iq2a_bank_reset(iq2a_bank* b) {
     b->ring_frames = 0;
     for (auto& sl : b->slot) sl.done_valid = false;
     std::fill(b->phase.begin(), b->phase.end(), 0.0);
+    b->phase_hist.clear();
     return fresh_state(b);
 }
 
@@ -861,8 +882,12 @@ int iq2a_bank_copy_gtable(const iq2a_bank* b, float* host_out, int64_t n_complex
 // kernels + D2H of the results on the compute stream; collect() waits for the oldest chunk and hands
 // its results over.  H2D of chunk k+1 overlaps the kernels and the D2H of chunk k.
 int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, int32_t want) {
+    return iq2a_bank_submit_chunks(b, frames, n_frames, 0, want);
+}
+
+int iq2a_bank_submit_chunks(iq2a_bank* b, const void* frames, int64_t n_frames, int64_t chunk_frames, int32_t want) {
     if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
-    if (n_frames < 0 || (n_frames > 0 && !frames)) { set_error("bad frame buffer"); return IQ2A_ERR_INVALID; }
+    if (n_frames < 0 || (n_frames > 0 && !frames) || chunk_frames < 0) { set_error("bad frame buffer"); return IQ2A_ERR_INVALID; }
     if (b->inflight >= 2) { set_error("two chunks already in flight: collect one first"); return IQ2A_ERR_STATE; }
     IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
     const int C = b->C, D = b->D;
@@ -877,8 +902,15 @@ int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, i
     const int64_t mg_begin = ceil_div(b->n_pos, D);
     const int64_t mg_end = ceil_div(b->n_pos + n_frames, D);
     const int64_t rows = mg_end - mg_begin;
+    // reference chunks covered by this call: the NCO phase wraps, the AGC restarts and the statistics windows begin at
+    // every multiple of chunk_frames from the call's first sample (chunk_frames == 0: the whole call is one chunk)
+    const int64_t cf = chunk_frames > 0 ? chunk_frames : std::max<int64_t>(n_frames, 1);
+    const int nseg = (int)std::max<int64_t>(1, ceil_div(n_frames, cf));
     sl.rows = rows;
     sl.n_frames = n_frames;
+    sl.n0 = b->n_pos;
+    sl.chunk_frames = cf;
+    sl.nwin = nseg;
     sl.want = want;
     b->submitted++;
     b->inflight++;
@@ -932,12 +964,30 @@ int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, i
     a.mg_begin = a.mg_emit = mg_begin;
     a.mg_end = mg_end;
     a.fresh = false;
-    a.seg_origin = b->n_pos;          // one call == one reference chunk
-    a.seg_len = std::max<int64_t>(n_frames, 1);
-    a.nseg = 1;
-    a.h_phase = b->phase.data();
+    // the reference's phase carry (processing.py:295) chunk by chunk: start phase of every reference chunk of the call
+    std::vector<double> hp((size_t)C * nseg);
+    for (int c = 0; c < C; ++c) {
+        double ph = b->phase[c];
+        for (int k = 0; k < nseg; ++k) {
+            hp[(size_t)c * nseg + k] = ph;
+            const int64_t len = std::min<int64_t>(cf, n_frames - (int64_t)k * cf);
+            ph = py_fmod(ph + b->w[c] * (double)len, 2.0 * M_PI);
+        }
+        b->phase[c] = ph;
+    }
+    for (int k = 0; k < nseg; ++k) {
+        std::vector<double> ph(C);
+        for (int c = 0; c < C; ++c) ph[c] = hp[(size_t)c * nseg + k];
+        b->phase_hist.emplace_back(b->n_pos + (int64_t)k * cf, std::move(ph));
+    }
+    while ((int)b->phase_hist.size() > 2 * kMixHist) b->phase_hist.pop_front();
+    a.use_hist = true;
+    a.seg_origin = b->n_pos;
+    a.seg_len = cf;
+    a.nseg = nseg;
+    a.h_phase = hp.data();            // staged by the runtime before cudaMemcpyAsync returns (pageable source)
     a.win0 = 0;
-    a.nwin = rows > 0 ? 1 : 0;
+    a.nwin = rows > 0 ? nseg : 0;
     a.d_audio = b->d_audio;
     a.d_clip = b->d_clip;
     a.d_bb_out = nullptr;
@@ -945,14 +995,12 @@ int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, i
     a.st = b->stream;
     if (rows > 0 && (rc = run_core(b, a))) return rc;
 
-    // the reference's phase carry (processing.py:295), and the sample counter
-    for (int c = 0; c < C; ++c) b->phase[c] = py_fmod(b->phase[c] + b->w[c] * (double)n_frames, 2.0 * M_PI);
     b->n_pos += n_frames;
 
     if (rows > 0) {
         // results -> pinned slot buffers (D2H on the compute stream, behind the kernels)
         const size_t nfl = (size_t)C * rows;
-        if ((rc = sl.ensure(nfl, C))) return rc;
+        if ((rc = sl.ensure(nfl, C * nseg))) return rc;
         if (want & 1)
             IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_audio, b->d_audio, nfl * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
         if (want & 2)
@@ -962,7 +1010,7 @@ int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, i
             IQ2A_CUDA_TRY(cudaMemcpy2DAsync(sl.h_bb, rows * sizeof(float2), b->d_bb, stride * sizeof(float2),
                                             rows * sizeof(float2), C, cudaMemcpyDeviceToHost, b->stream));
         }
-        IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_ss, b->d_sumsq, C * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        IQ2A_CUDA_TRY(cudaMemcpyAsync(sl.h_ss, b->d_sumsq, (size_t)C * nseg * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     }
     IQ2A_CUDA_TRY(cudaEventRecord(sl.done, b->stream));
     sl.done_valid = true;
@@ -971,17 +1019,30 @@ int iq2a_bank_submit_chunk(iq2a_bank* b, const void* frames, int64_t n_frames, i
 
 int iq2a_bank_collect_chunk(iq2a_bank* b, float* audio, float* clipped, float* baseband, int64_t out_stride,
                             int64_t* n_out, double* rms_dbfs) {
+    if (b && b->inflight > 0 && b->slot[(int)(b->collected & 1)].nwin > 1 && rms_dbfs) {
+        set_error("the oldest call covers %d reference chunks: collect it with iq2a_bank_collect_chunks", b->slot[(int)(b->collected & 1)].nwin);
+        return IQ2A_ERR_STATE;
+    }
+    return iq2a_bank_collect_chunks(b, audio, clipped, baseband, out_stride, n_out, rms_dbfs, 1, nullptr, nullptr);
+}
+
+int iq2a_bank_collect_chunks(iq2a_bank* b, float* audio, float* clipped, float* baseband, int64_t out_stride,
+                             int64_t* n_out, double* rms_dbfs, int64_t rms_capacity, int64_t* window_rows,
+                             int64_t* n_windows) {
     if (!b) { set_error("null bank"); return IQ2A_ERR_INVALID; }
     if (b->inflight <= 0) { set_error("no chunk in flight"); return IQ2A_ERR_STATE; }
     IQ2A_CUDA_TRY(cudaSetDevice(b->cfg.device));
     StreamSlot& sl = b->slot[(int)(b->collected & 1)];
-    b->collected++;
-    b->inflight--;
     const int C = b->C;
     const int64_t rows = sl.rows;
-    if (n_out) *n_out = rows;
-    if (sl.n_frames == 0) return IQ2A_OK;
+    const int nwin = sl.n_frames > 0 ? sl.nwin : 0;
+    if ((rms_dbfs || window_rows) && rms_capacity < nwin) { set_error("statistics buffers hold %lld windows, the call has %d", (long long)rms_capacity, nwin); return IQ2A_ERR_INVALID; }
     if (rows > out_stride && (audio || clipped || baseband)) { set_error("output stride %lld < %lld rows", (long long)out_stride, (long long)rows); return IQ2A_ERR_INVALID; }
+    b->collected++;
+    b->inflight--;
+    if (n_out) *n_out = rows;
+    if (n_windows) *n_windows = nwin;
+    if (sl.n_frames == 0) return IQ2A_OK;
     IQ2A_CUDA_TRY(cudaEventSynchronize(sl.done));
     collect_timing(b);
     if (rows > 0) {
@@ -991,11 +1052,17 @@ int iq2a_bank_collect_chunk(iq2a_bank* b, float* audio, float* clipped, float* b
             if (baseband && (sl.want & 4)) std::memcpy(baseband + 2 * (size_t)c * out_stride, sl.h_bb + (size_t)c * rows, rows * sizeof(float2));
         }
     }
+    // rows of every reference chunk of the call (Decimator.process output sizes) and its DecoderStats.rms_dbfs
+    std::vector<int64_t> cnt(std::max(nwin, 1), 0);
+    for (int k = 0; k < nwin; ++k) {
+        const int64_t lo = sl.n0 + (int64_t)k * sl.chunk_frames, hi = std::min(lo + sl.chunk_frames, sl.n0 + sl.n_frames);
+        cnt[k] = ceil_div(hi, b->D) - ceil_div(lo, b->D);
+        if (window_rows) window_rows[k] = cnt[k];
+    }
     if (rms_dbfs) {
-        std::vector<int64_t> cnt(C, rows);
-        std::vector<double> ss(C, 0.0);
-        if (rows > 0) std::memcpy(ss.data(), sl.h_ss, C * sizeof(double));
-        stats_to_dbfs(ss.data(), cnt.data(), C, rms_dbfs);
+        std::vector<double> ss((size_t)C * std::max(nwin, 1), 0.0);
+        if (rows > 0) std::memcpy(ss.data(), sl.h_ss, (size_t)C * nwin * sizeof(double));
+        for (int c = 0; c < C; ++c) stats_to_dbfs(ss.data() + (size_t)c * nwin, cnt.data(), nwin, rms_dbfs + (size_t)c * rms_capacity);
     }
     return IQ2A_OK;
 }

@@ -46,7 +46,14 @@ __global__ void __launch_bounds__(256) k_mix_exact(const MixExactParams p) {
     const int64_t f = n - p.raw_n0;
     if (n >= 0 && f >= 0 && f < p.raw_len) {
         const float2 x = raw_to_c64<FMT>(rp[f], p.iq_swap, p.q_neg);
-        const double ph = nco_phase(p.phase, p.chan, p.w, n);
+        double ph;
+        if (n >= p.phase.seg0_n || p.nhist == 0) {
+            ph = nco_phase(p.phase, p.chan, p.w, n);
+        } else {
+            int i = p.nhist - 1;
+            while (i > 0 && n < p.hist_start[i]) --i;
+            ph = __dadd_rn(p.hist_phase[i], __dmul_rn(p.w, (double)(n - p.hist_start[i])));
+        }
         double s, c;
         sincos(ph, &s, &c);
         out = cmul_np2(x, make_float2((float)c, (float)s));
@@ -335,10 +342,21 @@ __device__ __forceinline__ void dc_rows_warp(const float* __restrict__ x, float*
         if (lane == 0) xprev = x1;
         const float diff = __fsub_rn(xv, xprev);
         float mine = 0.f;
-        for (int j = 0; j < cnt; ++j) {
-            const float dj = __shfl_sync(0xffffffffu, diff, j);
-            y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
-            if (lane == j) mine = y1;
+        if (cnt == 32) {
+            // full group: the 32 shuffles do not depend on the carried value, so with the loop unrolled they are all
+            // in flight before the chain of 32 x (FMUL, FADD) starts -- the chain is what remains (8 cycles per row)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float dj = __shfl_sync(0xffffffffu, diff, j);
+                y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
+                if (lane == j) mine = y1;
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const float dj = __shfl_sync(0xffffffffu, diff, j);
+                y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
+                if (lane == j) mine = y1;
+            }
         }
         if (y_out && r < b) y_out[r] = mine;
         x1 = __shfl_sync(0xffffffffu, xv, cnt - 1);
@@ -439,10 +457,20 @@ __global__ void __launch_bounds__(32) k_seq_agc(const SeqParams p) {
         const float desired = live ? __fdiv_rn(target, mag) : 0.f;
         const unsigned mask = __ballot_sync(0xffffffffu, live);
         float mine = 1.0f;
-        for (int j = 0; j < cnt; ++j) {
-            const float dj = __shfl_sync(0xffffffffu, desired, j);
-            if (mask & (1u << j)) gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
-            if (lane == j) mine = gain;
+        if (cnt == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float dj = __shfl_sync(0xffffffffu, desired, j);
+                const float g2 = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
+                gain = (mask & (1u << j)) ? g2 : gain;
+                if (lane == j) mine = gain;
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const float dj = __shfl_sync(0xffffffffu, desired, j);
+                if (mask & (1u << j)) gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
+                if (lane == j) mine = gain;
+            }
         }
         if (r >= rec.hi || r < p.n_skip) continue;
         const float o = __fmul_rn(sv, mine);

@@ -5,6 +5,8 @@
 
 namespace iq2a {
 
+constexpr int kMixHist = 16;
+
 struct MixExactParams {
     const void* raw;
     int64_t raw_n0, raw_len;
@@ -15,6 +17,13 @@ struct MixExactParams {
     int chan;
     double w;
     float2* mixed;
+    // streaming: reference chunks of EARLIER calls whose samples are mixed again as filter history.  The reference
+    // mixed them with their own chunk's start phase (processing.py:292-295), and tab[0] + w * (negative offset)
+    // differs from that by the rounding of a ~1e5 rad product -- enough to move ~1e-3 of the complex64 LO values by
+    // one ulp.  Newest last; samples older than hist_start[0] extrapolate from it.
+    int nhist;
+    int64_t hist_start[kMixHist];
+    double hist_phase[kMixHist];
 };
 
 struct SeqChunk {

@@ -154,8 +154,11 @@ class IQReader:
     iterating yields complex64 blocks with the IQ order applied, like the reference, by running the
     unpack kernel with a zero-frequency oscillator."""
 
+    #: buffers of the pinned read ring: the chunk being filled + the (at most) two ChannelBank.stream has in flight
+    RING_DEPTH = 3
+
     def __init__(self, path: Path, chunk_size: int, iq_order: str, input_format: InputFormat, *,
-                 sample_rate: float | None = None):
+                 sample_rate: float | None = None, pinned: bool = False, batch: int = 1):
         if iq_order not in _lib.ORDER_IDS:
             raise ValueError(f"Unsupported iq_order '{iq_order}'")
         self.path = Path(path)
@@ -164,26 +167,57 @@ class IQReader:
         self.input_format = input_format
         self.sample_rate = sample_rate
         self.input_bytes_per_frame = input_format.bytes_per_frame
+        self.batch = max(1, int(batch))          # reference chunks per read_raw_block(batched=True)
+        self.pinned = bool(pinned)
         self._fh = None
+        self._ring: list[np.ndarray] = []
+        self._ring_ptrs: list[int] = []
+        self._slot = 0
 
     def __enter__(self) -> "IQReader":
         if self.input_format.container == "raw" and not (self.sample_rate and self.sample_rate > 0):
             raise ValueError("Raw IQ inputs require a sample rate override. Provide --input-sample-rate.")
         self._fh = self.path.open("rb", buffering=0)
         self._fh.seek(self.input_format.data_offset)
+        if self.pinned:
+            # page-locked ring (iq2a_host_alloc): the file is read straight into the memory the H2D copy engine
+            # takes it from -- no pageable staging copy inside the driver, the copy of chunk k+1 really overlaps
+            # the kernels of chunk k (the reference reads through an ffmpeg pipe, processing.py:238-259)
+            import ctypes as C
+            lib = _lib.load()
+            nbytes = self.chunk_size * self.batch * self.input_bytes_per_frame
+            for _ in range(self.RING_DEPTH):
+                p = C.c_void_p()
+                _lib.check(lib.iq2a_host_alloc(C.byref(p), nbytes))
+                self._ring_ptrs.append(p.value)
+                self._ring.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,)))
         return self
 
     def __exit__(self, *exc) -> None:
         if self._fh:
             self._fh.close()
             self._fh = None
+        if self._ring_ptrs:
+            lib = _lib.load()
+            self._ring = []
+            for p in self._ring_ptrs:
+                lib.iq2a_host_free(p)
+            self._ring_ptrs = []
 
-    def read_raw_block(self, max_frames: int | None = None) -> np.ndarray | None:
+    def read_raw_block(self, max_frames: int | None = None, *, batched: bool = False) -> np.ndarray | None:
+        """Next chunk of PCM payload bytes (None at the end of the capture); `batched`: up to `batch` reference
+        chunks at once.  With a pinned ring the returned view is valid until RING_DEPTH - 1 further reads."""
         if self._fh is None:
             raise RuntimeError("IQReader has not been entered.")
-        frames = self.chunk_size if max_frames is None else min(self.chunk_size, max_frames)
+        frames = self.chunk_size * (self.batch if batched else 1)
+        if max_frames is not None:
+            frames = min(frames, max_frames)
         fb = self.input_bytes_per_frame
-        buf = np.empty(frames * fb, dtype=np.uint8)
+        if self._ring:
+            buf = self._ring[self._slot][:frames * fb]
+            self._slot = (self._slot + 1) % len(self._ring)
+        else:
+            buf = np.empty(frames * fb, dtype=np.uint8)
         got = self._fh.readinto(memoryview(buf))
         while 0 < got < buf.size:
             more = self._fh.readinto(memoryview(buf)[got:])
@@ -546,7 +580,16 @@ class ProcessingPipeline:
         results: list[ProcessingResult] = []
         processed = 0
         try:
-            with IQReader(Path(cfg.in_path), chunk, cfg.iq_order, fmt, sample_rate=sample_rate) as reader:
+            # reference chunks per GPU call: enough rows to fill the persistent kernel's CTA slots at high decimation
+            # (one 4 Mi-sample chunk at D = 640 is 7 block sets for 296 slots), bounded by 128 MiB of pinned ring
+            # -- about 48 k channel-rate rows per call; a 10 MS/s capture already has 40 k rows per chunk and stays at 2
+            batch = max(1, min(8, -(-49_152 * decimation // max(chunk, 1)), (128 << 20) // max(chunk * fmt.bytes_per_frame, 1)))
+            if os.environ.get("IQ2A_BIND_NUMA", "1") != "0":
+                # the reader thread and the pinned ring next to the GPU's PCIe root (numa.py); affects this thread only
+                from .numa import bind_to_device_numa
+                LOG.debug("host placement: %s", bind_to_device_numa(cfg.device))
+            with IQReader(Path(cfg.in_path), chunk, cfg.iq_order, fmt, sample_rate=sample_rate, pinned=True,
+                          batch=batch) as reader:
                 self._check_cancel("initialization")
                 first = reader.read_raw_block(max_samples)
                 if first is None:
@@ -596,11 +639,11 @@ class ProcessingPipeline:
                         left = None if max_samples is None else max_samples - processed
                         if left is not None and left <= 0:
                             break
-                        blk = reader.read_raw_block(left)
+                        blk = reader.read_raw_block(left, batched=True)
 
                 with bank:
                     for res in bank.stream(blocks(), want_baseband=want_bb, want_audio=False,
-                                           want_clipped=not pass_through):
+                                           want_clipped=not pass_through, chunk_frames=chunk):
                         prog.advance("channel", float(res.count))
                         for fd, row in zip(dumps, res.baseband if dumps else ()):   # IQDebugWriter, :363-378
                             fd.write(row.tobytes())

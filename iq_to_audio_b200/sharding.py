@@ -284,12 +284,16 @@ class PeerWriters:
     device-to-device copy per target on a side stream.  A writer takes in only its own targets -- (world-1)/world
     of ONE target per shard instead of everything -- so the many-to-one congestion that sank the push to rank 0 at
     N = 8 does not arise, and because copy engines do the moving the persistent channel-bank kernel keeps every SM
-    (the NCCL exchange needs 16 of them reserved).  Ordering is PeerGather's, with every owning rank a consumer:
+    (the NCCL exchange needs 16 of them reserved).  Nothing on the COMPUTE stream waits for another rank:
 
-        compute stream :  compute(k) -> wait push(k-1) -> [owner: wait consume(k-2)] -> barrier(k) -> compute(k+1)
-        side stream    :  wait compute(k) -> push(k)          owner: wait barrier(k) -> consume(k-1)
+        compute stream :  wait push(k-3) done (own slot free) -> compute(k)
+        side stream    :  wait compute(k) -> push(k) -> barrier(k) -> [owner: consume(k)]
 
-    Once barrier(k) has passed, every push(k-1) has landed everywhere; three slots make reuse strict.
+    barrier(k) (signal pads of the symmetric allocation) runs on the side stream: once it has passed, every push(k)
+    has landed everywhere and the owner may read slot k % 3; a pusher reaches push(k+3) only after barrier(k+2), by
+    which time every owner has consumed step k, so slot reuse is safe without any cross-rank wait in the compute
+    path.  (Round 1 had the barrier on the compute stream between two steps: every step then took the maximum over
+    the ranks plus the barrier's latency, 2.41 -> 2.64 ms at N = 8.)  The ranks may drift up to three steps apart.
     """
 
     DEPTH = 3
@@ -342,30 +346,15 @@ class PeerWriters:
                 self.dest[s][c].copy_(self.local[s][c], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.side)
+            self.hdl.barrier(channel=0)                   # every push of step k has landed on every writer
+            if self.owned:
+                if self.consumer is not None:
+                    self.consumer(k, self.result(k))
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+                self.consumed[k] = ev
+                self.consumed.pop(k - self.DEPTH, None)
         self.pushed[k] = done
-        prev = self.pushed.get(k - 1)
-        if prev is not None:
-            stream.wait_event(prev)
-        if self.owned:
-            old = self.consumed.pop(k - 2, None)
-            if old is not None:
-                stream.wait_event(old)
-        with torch.cuda.stream(stream):
-            self.hdl.barrier(channel=0)
-        if self.owned and k >= 1:
-            landed = torch.cuda.Event()
-            landed.record(stream)
-            self._consume(k - 1, landed)
-
-    def _consume(self, k: int, after) -> None:
-        torch = self.torch
-        self.side.wait_event(after)
-        with torch.cuda.stream(self.side):
-            if self.consumer is not None:
-                self.consumer(k, self.result(k))
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-        self.consumed[k] = ev
 
     def result(self, k: int) -> dict:
         """{target: [world, rows]} for the targets this rank writes (rows of shard s in row s)."""
@@ -376,6 +365,3 @@ class PeerWriters:
         stream.synchronize()
         self.side.synchronize()
         self.dist.barrier()
-        if self.owned and last_step >= 0 and last_step not in self.consumed:
-            self._consume(last_step, self.torch.cuda.Event())
-            self.side.synchronize()

@@ -346,6 +346,47 @@ def test_pipelined_stream_equals_synchronous_chunks(gpu):
         np.testing.assert_allclose(a[3], b[3], rtol=0, atol=1e-9)   # float64 atomics: summation order varies
 
 
+def test_batched_stream_keeps_reference_chunk_semantics(gpu):
+    """ChannelBank.stream(..., chunk_frames=): several reference chunks per GPU call.  Phase wraps, AGC restarts and
+    DecoderStats stay per reference chunk, so the result equals the one-chunk-per-call run (the block grid of the
+    transforms moves with the call, hence float32 rounding and not bit equality on the fast path).  USB with AGC on
+    is on the bit-faithful path: both ways of calling must reproduce the ORACLE bit for bit -- which needs the
+    filter history of a call to be mixed with the phase of the chunk it belonged to (the reference mixed it then),
+    not with a phase extrapolated backwards from the current chunk."""
+    fs = 10e6
+    d, fs_ch = orc.plan_decimation(fs, 96_000.0)
+    n = 1_900_037
+    carriers = [dict(offset=1.0e6, amp=0.2, kind="fm", tone=700.0, dev=2500.0), dict(offset=-2.2e6, amp=0.2, kind="am", tone=800.0),
+                dict(offset=3.05e6, amp=0.2, kind="usb", tone=900.0)]
+    raw = orc.to_s16(orc.multi_carrier_capture(fs, n, carriers, noise_std=0.01, seed=11))
+    T = gpu["Target"]
+    tg = [T(1.0e6, orc.channel_taps(fs, 12_500.0, d), 1, "nfm"), T(-2.2e6, orc.channel_taps(fs, 10_000.0, d), 1, "am"),
+          T(3.05e6, orc.channel_taps(fs, 2_800.0, d), -1, "usb", 300.0, True)]
+    chunk = 1 << 18
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=chunk) as bank:
+        one = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, n)]) for s in range(0, n, chunk)]
+    a1 = np.concatenate([r.audio for r in one], axis=1)
+    c1 = np.concatenate([r.clipped for r in one], axis=1)
+    rms1 = np.stack([r.rms_dbfs for r in one], axis=1)
+    cnt1 = np.array([r.count for r in one])
+    with gpu["ChannelBank"](fs, d, tg, ref_chunk=chunk) as bank:
+        k = 3                                                    # 3 reference chunks per call, a ragged last call
+        views = [raw[2 * s:2 * min(s + k * chunk, n)] for s in range(0, n, k * chunk)]
+        many = list(bank.stream(views, chunk_frames=chunk))
+    a2 = np.concatenate([r.audio for r in many], axis=1)
+    c2 = np.concatenate([r.clipped for r in many], axis=1)
+    rms2 = np.concatenate([r.rms_dbfs for r in many], axis=1)
+    cnt2 = np.concatenate([r.window_counts for r in many])
+    assert np.array_equal(cnt1, cnt2) and a1.shape == a2.shape and rms1.shape == rms2.shape
+    assert np.abs(a1[:2] - a2[:2]).max() <= 2e-6 and np.abs(c1[:2] - c2[:2]).max() <= 2e-6
+    assert np.abs(rms1 - rms2).max() <= 1e-4
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    plan = orc.TargetPlan(sample_rate=fs, freq_offset=3.05e6, bandwidth=2_800.0, mode="usb", agc_enabled=True, mix_sign=-1)
+    want = orc.run_target(x, plan, chunk)
+    for audio, clipped in ((a1[2], c1[2]), (a2[2], c2[2])):
+        assert np.array_equal(audio, want.audio) and np.array_equal(clipped, want.clipped)
+
+
 def test_chunk_split_invariance_and_state_roundtrip(gpu):
     """Feeding the same capture in different call sizes gives the same audio (NFM has no per-chunk
     semantics); get_state/set_state moves the carried decoder state between banks."""

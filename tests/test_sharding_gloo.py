@@ -191,3 +191,13 @@ def test_writer_place_covers_every_receive_area_exactly_once():
             for r in range(world):
                 owned = len([c for c in range(C) if c % world == r])
                 assert len(seen[r]) == depth * owned * world
+
+
+def test_numa_helpers_are_safe_without_a_gpu():
+    """numa.bind_to_device_numa is a no-op (and says so) when the topology is unknown -- e.g. in this CPU container."""
+    from iq_to_audio_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = numa.bind_to_device_numa(0)
+    assert info["device"] == 0 and (info["bound"] or os.sched_getaffinity(0) == before)
