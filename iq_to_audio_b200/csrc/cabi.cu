@@ -137,6 +137,11 @@ struct iq2a_bank {
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     int* d_setctr = nullptr;        // block-set counter of the generation-5 kernel (dynamic scheduling)
+    // many-channel form (channelizer5s.cuh): forward transforms once per wave of block sets, groups of <= 4 channels
+    bool many_ok = false;
+    SplitGroup* d_split_groups = nullptr;
+    double* d_phase_bias = nullptr;
+    float4* d_scratch = nullptr;    size_t scratch_cap = 0;
     float4* d_gtab5 = nullptr;      // mirror-pair table of the generation-5 kernel (channelizer5.cuh)
     bool pair_ok = false;           // at least one group on the mirror-pair kernel
     bool v2_ok = false;
@@ -176,7 +181,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_setctr, d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_split_groups, d_phase_bias, d_scratch, d_setctr, d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -285,6 +290,43 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     const bool use_cp = !use_v2 && b->cp_ok;
     if (use_cp) mg_split = a.mg_end;
     else if (!use_v2) mg_split = a.mg_begin;
+    const bool use_many = use_v2 && b->many_ok;
+    if (use_many) {
+        // every channel group in one pass: forward transforms once per wave of block sets (channelizer5s.cuh)
+        ChannelizeParams p{};
+        p.raw = a.d_raw;
+        p.raw_n0 = a.raw_n0;
+        p.raw_len = a.raw_len;
+        p.iq_swap = swap;
+        p.q_neg = neg;
+        p.decim = b->D;
+        p.vd = b->vd;
+        p.ld = b->ld;
+        p.twid = b->d_tw;
+        p.out_stride = stride;
+        p.phase.seg_len = a.seg_len;
+        p.phase.seg0_n = a.seg_origin;
+        p.phase.nseg = a.nseg;
+        p.mg_begin = a.mg_begin;
+        p.mg_end = mg_split;
+        p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
+        const PairGeo& geo = b->groups[0].pair;
+        const size_t per_set = channelize5_scratch_bytes_per_set(geo);
+        const int nsets = (p.nblocks + 1) / 2;
+        const int wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)nsets, ((size_t)96 << 20) / per_set));
+        if ((rc = dev_grow(&b->d_scratch, &b->scratch_cap, (size_t)wave * per_set / sizeof(float4)))) return rc;
+        SplitParams sp{};
+        sp.scratch = b->d_scratch;
+        sp.groups = b->d_split_groups;
+        sp.gtab5 = b->d_gtab5;
+        sp.w = b->d_w;
+        sp.phase_bias = b->d_phase_bias;
+        sp.rot = b->d_rot;
+        sp.phase_tab = b->d_phase;
+        sp.out = b->d_bb;
+        if ((rc = launch_channelize5_many(p, geo, t_base, t_row0, t_rows, sp, (int)b->groups.size(), 4, wave, b->n_sm, a.st, &b->launches))) return rc;
+        b->launches_v2++;
+    }
     for (const Group& g : b->groups) {
         if (g.skip) continue;                        // bit-faithful channels only: precise.cu below computes them
         ChannelizeParams p{};
@@ -305,7 +347,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         p.phase.seg0_n = a.seg_origin;
         p.phase.nseg = a.nseg;
         for (int i = 0; i < g.count; ++i) p.w[i] = b->w[g.first + i];
-        if (use_v2 || use_cp) {
+        if ((use_v2 || use_cp) && !use_many) {
             p.mg_begin = a.mg_begin;
             p.mg_end = mg_split;
             p.nblocks = (int)ceil_div(mg_split - a.mg_begin, b->ld);
@@ -637,7 +679,19 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     // channel groups: runs of consecutive channels with the same filter length on the same path (fast / bit-faithful),
     // each run in groups of <= gmax channels -- so that a group can take the mirror-pair kernel with its own geometry
     // and a group of bit-faithful channels is not computed twice; too many runs: plain groups of consecutive channels
-    const int gmax = channelize_max_group(M);
+    // 25+ channels of one filter on the int16 / TMA path (5+ launches of the fused kernel): the many-channel form, whose multiply-accumulate kernel
+    // takes groups of <= 4 channels (IQ2A_MANY=0 keeps the fused kernel)
+    bool many = false;
+    {
+        const char* env = std::getenv("IQ2A_CHANNELIZER");
+        const char* em = std::getenv("IQ2A_MANY");
+        many = C >= 25 && M == 512 && cfg->codec == IQ2A_CODEC_S16 && D % 4 == 0 && channelize2_available() && !env &&
+               !(em && std::strcmp(em, "0") == 0) && b->precise.empty();
+        for (int c = 1; c < C && many; ++c) many = tn[c] == tn[0];
+        PairGeo probe{};
+        many = many && pair_geometry(tn[0], D, &probe);
+    }
+    const int gmax = many ? 4 : channelize_max_group(M);
     size_t g_total = 0;
     {
         std::vector<std::pair<int, int>> runs;                 // (first, count)
@@ -744,6 +798,22 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             }
         }
         b->kernel_gen = b->pair_ok ? 5 : ((b->v2_ok || b->cp_ok) ? 4 : 1);
+        b->many_ok = many;
+        for (const Group& g : b->groups) b->many_ok = b->many_ok && g.pair_ok;
+        if (b->many_ok) {
+            std::vector<SplitGroup> sg;
+            for (const Group& g : b->groups) sg.push_back(SplitGroup{g.first, g.count, g.g5_off});
+            std::vector<double> bias(C);
+            const double half_len = 0.5 * (double)(tn[0] - 1);
+            for (int c = 0; c < C; ++c) bias[c] = py_fmod(-b->w[c] * half_len, 2.0 * M_PI);
+            if ((rc = dev_alloc(&b->d_split_groups, sg.size())) || (rc = dev_alloc(&b->d_phase_bias, (size_t)C))) { cudaFree(d_wtab); return fail(rc); }
+            if (cudaMemcpy(b->d_split_groups, sg.data(), sg.size() * sizeof(SplitGroup), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(b->d_phase_bias, bias.data(), C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(d_wtab);
+                set_error("table upload failed");
+                return fail(IQ2A_ERR_CUDA);
+            }
+        }
         if ((b->v2_ok || b->cp_ok) && (rc = dev_alloc(&b->d_gtab2, g_total))) { cudaFree(d_wtab); return fail(rc); }
         if (b->pair_ok && ((rc = dev_alloc(&b->d_gtab5, g5_total)) || (rc = dev_alloc(&b->d_setctr, (size_t)1)))) { cudaFree(d_wtab); return fail(rc); }
     }

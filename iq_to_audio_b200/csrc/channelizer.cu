@@ -124,6 +124,24 @@ int launch_channelize5(const ChannelizeParams& p, int cg, const PairGeo& geo, co
     return IQ2A_ERR_INVALID;
 }
 
+int launch_channelize5_split(const ChannelizeParams& p, const PairMaps& maps, const PairGeo& geo, int64_t tmap_row0,
+                             SplitParams sp, int ngroups, int cg_max, int wave_sets, int cta_slots, cudaStream_t st, int64_t* launches);
+
+size_t channelize5_scratch_bytes_per_set(const PairGeo& geo) { return (size_t)geo.ntiles * 16 * 256 * sizeof(float4); }
+
+int launch_channelize5_many(const ChannelizeParams& p, const PairGeo& geo, const void* base, int64_t tmap_row0, int64_t rows,
+                            const SplitParams& sp, int ngroups, int cg_max, int wave_sets, int n_sm, cudaStream_t st, int64_t* launches) {
+    if (p.nblocks <= 0) return IQ2A_OK;
+    PairMaps maps;
+    int rc;
+    if ((rc = encode_rows_map(&maps.fwd, base, p.decim, rows, 4, kFwdBoxRows))) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = encode_rows_map(&maps.wrap[k], base, p.decim, rows, 4, geo.hw[k]))) return rc;
+        if ((rc = encode_rows_map(&maps.lin[k], base, p.decim, rows, 4, geo.hl[k]))) return rc;
+    }
+    return launch_channelize5_split(p, maps, geo, tmap_row0, sp, ngroups, cg_max, wave_sets, 2 * n_sm, st, launches);
+}
+
 // Generation-4 kernel with cp.async staging: no tensor map, the kernel bounds-checks against p.raw_n0 / p.raw_len.
 int launch_channelize2_cp(const ChannelizeParams& p, int cg, int n_sm, cudaStream_t st) {
     if (p.nblocks <= 0) return IQ2A_OK;

@@ -44,6 +44,182 @@ struct Geo5 {
     static constexpr size_t smem = tile_bytes + 4 * (size_t)kRegionBytes + orph_bytes + 256 * sizeof(float2) + 32;
 };
 
+// ---- pieces shared by the fused kernel (k_channelize5) and the split kernels (channelizer5s.cuh) ----------------
+
+// int16 -> float without the (quarter-rate) I2F unit: see channelizer2.cuh
+struct Unpack5 {
+    uint32_t xmask, exp_seed;
+    pk_t bias_q;
+    int iq_swap;
+};
+__device__ __forceinline__ Unpack5 make_unpack5(const ChannelizeParams& p) {
+    const uint32_t qmask = p.q_neg ? 0x7fffu : 0x8000u;
+    Unpack5 u;
+    u.xmask = p.iq_swap ? (0x80000000u | qmask) : ((qmask << 16) | 0x8000u);
+    u.bias_q = pk_bc(p.q_neg ? -8421375.0f : -8421376.0f);
+    u.exp_seed = 0x4B000000u + ((uint32_t)p.iq_swap >> 8);
+    u.iq_swap = p.iq_swap;
+    return u;
+}
+
+// The copy of tile t of the block set starting at block blk0 (one thread): per block 3 forward boxes, the wrap
+// box and 2 linear boxes of the mirror strip (header comment: staging).
+__device__ __forceinline__ void issue_tile5(unsigned char* stage, uint64_t* bar, const PairMaps& maps, const PairGeo& geo,
+                                            const ChannelizeParams& p, int64_t tmap_row0, int blk0, int t) {
+    const int cls = t >= geo.tiles1;
+    const int j = cls ? t - geo.tiles1 : t;
+    const int fwd = 4 * ((cls ? geo.g1 : 0) + j);                                  // forward group u
+    const int mir = 4 * ((cls ? geo.g1 + geo.g2 : geo.g1) - 1 - j);                // mirror group w
+    const int dm = cls ? geo.dm[1] : geo.dm[0], hw = cls ? geo.hw[1] : geo.hw[0], hl = cls ? geo.hl[1] : geo.hl[0];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)(2 * (3 * kFwdBoxRows + hw + 2 * hl) * 16));
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int64_t row0 = p.mg_begin + (int64_t)(blk0 + b) * p.ld - p.vd;
+        const int rw = (int)(row0 - tmap_row0);                // tensor row of window row 0
+        unsigned char* rf = stage + (b * 2) * kRegionBytes;
+        unsigned char* rm = rf + kRegionBytes;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            tma_load_2d(rf + k * kFwdBoxRows * 16, &maps.fwd, fwd, rw - (dm + 1) + k * kFwdBoxRows, bar);
+        // (one cp.async.bulk.tensor per descriptor in the source: the descriptor address stays uniform)
+        if (cls) {
+            // staging rows [0, hw) <- window rows [512 - hw, 512): rows dm.. are the wrapped part of the rotation
+            tma_load_2d(rm, &maps.wrap[1], mir, rw + 512 - hw, bar);
+            // staging rows [hw, hw + 2 hl) <- window rows [0, 2 hl)
+            tma_load_2d(rm + hw * 16, &maps.lin[1], mir, rw, bar);
+            tma_load_2d(rm + (hw + hl) * 16, &maps.lin[1], mir, rw + hl, bar);
+        } else {
+            tma_load_2d(rm, &maps.wrap[0], mir, rw + 512 - hw, bar);
+            tma_load_2d(rm + hw * 16, &maps.lin[0], mir, rw, bar);
+            tma_load_2d(rm + (hw + hl) * 16, &maps.lin[0], mir, rw + hl, bar);
+        }
+    }
+}
+
+// Pass 1 of a tile: two 16-point DIFs (even / odd rows) per thread, packed, twiddle, store to T[k1*16 + m2][slot].
+// `after_load` runs once the thread's rows are in registers (the staging buffer is free for this warp),
+// `before_store` before the first store (the tile must be free).
+template <class F1, class F2>
+__device__ __forceinline__ void pass1_5(const uint32_t* st, int m2p1, int slot, float4* T, const float2* tw256,
+                                        const Unpack5& u, F1&& after_load, F2&& before_store) {
+    constexpr int RS = 17;
+    const pk_t bias_i = pk_bc(-8421376.0f);
+    pk_t re[16], im[16];
+    auto unpack = [&](auto swapped) {
+        constexpr uint32_t sel_lo = 0x7610u, sel_hi = 0x7632u;
+        constexpr uint32_t sel_i = decltype(swapped)::value ? sel_hi : sel_lo;
+        constexpr uint32_t sel_q = decltype(swapped)::value ? sel_lo : sel_hi;
+        uint32_t ex = u.exp_seed;
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+            const int row = 32 * m1 + 2 * m2p1;
+            const uint32_t w0 = st[row * 4] ^ u.xmask, w1 = st[(row + 1) * 4] ^ u.xmask;
+            const uint32_t i0 = __byte_perm(w0, ex, sel_i), i1 = __byte_perm(w1, ex, sel_i);
+            const uint32_t q0 = __byte_perm(w0, ex, sel_q), q1 = __byte_perm(w1, ex, sel_q);
+            ex = i0;
+            re[m1] = pk_add(pk_make_u(i0, i1), bias_i);
+            im[m1] = pk_add(pk_make_u(q0, q1), u.bias_q);
+        }
+    };
+    if (u.iq_swap) unpack(std::true_type{});
+    else unpack(std::false_type{});
+    after_load();
+    pk_dif<16>(re, im);
+    const uint32_t dst = smem_u32(T) + (m2p1 * RS + slot) * 16;
+    static_for<16>([&](auto kc) {
+        constexpr int k1 = decltype(kc)::value;
+        if constexpr (k1 != 0) {
+            // W_256^{m2 k1}: an 8-byte load that the row groups of a warp share; ptxas turns the (w, w) pairs into
+            // scalar-broadcast operands of the packed ops
+            const pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
+            const float2 w = tw256[k1 * 16 + m2p1];
+            const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
+            re[bitrev<16>(k1)] = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
+            im[bitrev<16>(k1)] = pk_fma(xr, wi, pk_mul(xi, wr));
+        }
+    });
+    before_store();
+    static_for<16>([&](auto kc) {
+        constexpr int k1 = decltype(kc)::value;
+        sts64_at<16 * (k1 * 16) * RS>(dst, re[bitrev<16>(k1)]);
+        sts64_at<16 * (k1 * 16) * RS + 8>(dst, im[bitrev<16>(k1)]);
+    });
+}
+
+// Pass 2 of a tile: 16-point DIF over m2, in place (thread: column `slot`, rows k1*16 .. k1*16+15).
+__device__ __forceinline__ void pass2_5(float4* T, int k1, int slot) {
+    constexpr int RS = 17;
+    const uint32_t colp = smem_u32(T) + ((k1 * 16) * RS + slot) * 16;
+    pk_t re[16], im[16];
+    static_for<16>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const ulonglong2 v = lds128_at<16 * i * RS>(colp);
+        re[i] = v.x;
+        im[i] = v.y;
+    });
+    pk_dif<16>(re, im);
+    static_for<16>([&](auto kc) {
+        constexpr int k2 = decltype(kc)::value;
+        sts64_at<16 * k2 * RS>(colp, re[bitrev<16>(k2)]);
+        sts64_at<16 * k2 * RS + 8>(colp, im[bitrev<16>(k2)]);
+    });
+}
+
+// X[k'] = E + W O, X[k'+256] = E - W O of a packed (E, O) spectrum: both bins in one register pair
+__device__ __forceinline__ void radix2_5(float2 wc, pk_t e_o_re, pk_t e_o_im, pk_t& xr, pk_t& xi) {
+    float e_r, o_r, e_i, o_i;
+    pk_split(e_o_re, e_r, o_r);
+    pk_split(e_o_im, e_i, o_i);
+    const float pr = fmaf(wc.x, o_r, -wc.y * o_i), pi = fmaf(wc.x, o_i, wc.y * o_r);
+    xr = pk_make(e_r + pr, e_r - pr);
+    xi = pk_make(e_i + pi, e_i - pi);
+}
+
+// acc += a (Xf + Xm) + j b (Xf - Xm) for block b: table entry (a_k', a_k'+256, b_k', b_k'+256) per channel
+template <int CG, int BT>
+__device__ __forceinline__ void pair_mac5(pk_t (&acc)[2][CG][BT], int b, float2 wc, ulonglong2 vf, ulonglong2 vm,
+                                          const float4 (&g)[CG]) {
+    {
+        pk_t sr, si;
+        radix2_5(wc, pk_add(vf.x, vm.x), pk_add(vf.y, vm.y), sr, si);
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+            const pk_t ga = pk_make(g[c].x, g[c].y);
+            acc[0][c][b] = pk_fma(ga, sr, acc[0][c][b]);
+            acc[1][c][b] = pk_fma(ga, si, acc[1][c][b]);
+        }
+    }
+    {
+        pk_t dr, di;
+        radix2_5(wc, pk_sub(vf.x, vm.x), pk_sub(vf.y, vm.y), dr, di);
+        const pk_t ndi = di ^ 0x8000000080000000ull;       // sign flips: off the FMA pipe
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+            const pk_t gb = pk_make(g[c].z, g[c].w);
+            acc[0][c][b] = pk_fma(gb, ndi, acc[0][c][b]);
+            acc[1][c][b] = pk_fma(gb, dr, acc[1][c][b]);
+        }
+    }
+}
+
+// acc += e X for block b (plain complex product; entry (e.re_k', e.re_k'+256, e.im_k', e.im_k'+256)): the column
+// left over at the end of a class
+template <int CG, int BT>
+__device__ __forceinline__ void single_mac5(pk_t (&acc)[2][CG][BT], int b, float2 wc, ulonglong2 v, const float4 (&g)[CG]) {
+    pk_t xr, xi;
+    radix2_5(wc, v.x, v.y, xr, xi);
+    const pk_t nxi = xi ^ 0x8000000080000000ull;
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+        const pk_t er = pk_make(g[c].x, g[c].y), ei = pk_make(g[c].z, g[c].w);
+        acc[0][c][b] = pk_fma(er, xr, acc[0][c][b]);
+        acc[0][c][b] = pk_fma(ei, nxi, acc[0][c][b]);
+        acc[1][c][b] = pk_fma(er, xi, acc[1][c][b]);
+        acc[1][c][b] = pk_fma(ei, xr, acc[1][c][b]);
+    }
+}
+
 // Epilogue of a block set: inverse 512-point transforms of the CG x 2 output spectra, overlap rows dropped, NCO
 // rotation, complex64 store.  The thread that owns bins (k', k'+256) first does the radix-2 step of the inverse
 //   y[2n'+e] = sum_k' (Y[k'] + (-1)^e Y[k'+256]) W_512^{-e k'} W_256^{-n' k'},
@@ -196,10 +372,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     const float4* __restrict__ gtab = reinterpret_cast<const float4*>(p.gtab) + r_mac;
     const uint32_t orow = smem_u32(orph) + r_mac * 16;        // this thread's carried spectrum (block b: + b * 4096)
 
-    const uint32_t qmask = p.q_neg ? 0x7fffu : 0x8000u;
-    const uint32_t xmask = p.iq_swap ? (0x80000000u | qmask) : ((qmask << 16) | 0x8000u);
-    const pk_t bias_i = pk_bc(-8421376.0f), bias_q = pk_bc(p.q_neg ? -8421375.0f : -8421376.0f);
-    const uint32_t exp_seed = 0x4B000000u + ((uint32_t)p.iq_swap >> 8);
+    const Unpack5 unpack = make_unpack5(p);
 
     // staging word pointer of this thread per class (row offset df / dm folded in)
     const int tiles1 = geo.tiles1, ntiles = geo.ntiles;
@@ -221,143 +394,23 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
         // The copy of a tile is issued by ONE thread: at the start of a set thread 0, inside the loop lane 0 of the
         // last warp that has taken its rows out of the staging buffer (a counter in shared memory) -- as early as the
         // buffer is free, half a pass before the barrier that every warp waits at.
-        //   block b: 3 forward boxes, the wrap box, 2 linear boxes
-        auto issue = [&](int t) {
-            const int cls = t >= tiles1;
-            const int j = cls ? t - tiles1 : t;
-            const int fwd = 4 * ((cls ? geo.g1 : 0) + j);                                  // forward group u
-            const int mir = 4 * ((cls ? geo.g1 + geo.g2 : geo.g1) - 1 - j);                // mirror group w
-            const int dm = cls ? geo.dm[1] : geo.dm[0], hw = cls ? geo.hw[1] : geo.hw[0], hl = cls ? geo.hl[1] : geo.hl[0];
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, (uint32_t)(BT * (3 * kFwdBoxRows + hw + 2 * hl) * 16));
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                const int64_t row0 = p.mg_begin + (int64_t)(blk0 + b) * p.ld - p.vd;
-                const int rw = (int)(row0 - tmap_row0);                // tensor row of window row 0
-                unsigned char* rf = stage + (b * 2) * kRegionBytes;
-                unsigned char* rm = rf + kRegionBytes;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    tma_load_2d(rf + k * kFwdBoxRows * 16, &maps.fwd, fwd, rw - (dm + 1) + k * kFwdBoxRows, bar);
-                // (one cp.async.bulk.tensor per descriptor in the source: the descriptor address stays uniform)
-                if (cls) {
-                    // staging rows [0, hw) <- window rows [512 - hw, 512): rows dm.. are the wrapped part of the rotation
-                    tma_load_2d(rm, &maps.wrap[1], mir, rw + 512 - hw, bar);
-                    // staging rows [hw, hw + 2 hl) <- window rows [0, 2 hl)
-                    tma_load_2d(rm + hw * 16, &maps.lin[1], mir, rw, bar);
-                    tma_load_2d(rm + (hw + hl) * 16, &maps.lin[1], mir, rw + hl, bar);
-                } else {
-                    tma_load_2d(rm, &maps.wrap[0], mir, rw + 512 - hw, bar);
-                    tma_load_2d(rm + hw * 16, &maps.lin[0], mir, rw, bar);
-                    tma_load_2d(rm + (hw + hl) * 16, &maps.lin[0], mir, rw + hl, bar);
-                }
-            }
-        };
-        if (tid == 0) issue(0);
-
-        // X[k'] = E + W O, X[k'+256] = E - W O of a packed (E, O) spectrum: both bins in one register pair
-        auto radix2 = [&](pk_t e_o_re, pk_t e_o_im, pk_t& xr, pk_t& xi) {
-            float e_r, o_r, e_i, o_i;
-            pk_split(e_o_re, e_r, o_r);
-            pk_split(e_o_im, e_i, o_i);
-            const float pr = fmaf(wc.x, o_r, -wc.y * o_i), pi = fmaf(wc.x, o_i, wc.y * o_r);
-            xr = pk_make(e_r + pr, e_r - pr);
-            xi = pk_make(e_i + pi, e_i - pi);
-        };
-        // acc += a (Xf + Xm) + j b (Xf - Xm) for block b, table entry (a_k', a_k'+256, b_k', b_k'+256) per channel
-        auto pair_mac = [&](int b, ulonglong2 vf, ulonglong2 vm, const float4 (&g)[CG]) {
-            {
-                pk_t sr, si;
-                radix2(pk_add(vf.x, vm.x), pk_add(vf.y, vm.y), sr, si);
-#pragma unroll
-                for (int c = 0; c < CG; ++c) {
-                    const pk_t ga = pk_make(g[c].x, g[c].y);
-                    acc[0][c][b] = pk_fma(ga, sr, acc[0][c][b]);
-                    acc[1][c][b] = pk_fma(ga, si, acc[1][c][b]);
-                }
-            }
-            {
-                pk_t dr, di;
-                radix2(pk_sub(vf.x, vm.x), pk_sub(vf.y, vm.y), dr, di);
-                const pk_t ndi = di ^ 0x8000000080000000ull;       // sign flips: off the FMA pipe
-#pragma unroll
-                for (int c = 0; c < CG; ++c) {
-                    const pk_t gb = pk_make(g[c].z, g[c].w);
-                    acc[0][c][b] = pk_fma(gb, ndi, acc[0][c][b]);
-                    acc[1][c][b] = pk_fma(gb, dr, acc[1][c][b]);
-                }
-            }
-        };
+        if (tid == 0) issue_tile5(stage, bar, maps, geo, p, tmap_row0, blk0, 0);
 
         for (int t = 0; t < ntiles; ++t) {
             // every warp bumps s_ctl[0] once per tile after the wait below, so the tile's sequence number -- and with
             // it the phase of the barrier -- is s_ctl[0] / 8 for every thread that gets here (no register spent on it)
             mbar_wait(bar, ((uint32_t)*reinterpret_cast<volatile int*>(s_ctl) >> 3) & 1u);
-            // ------------- pass 1: two 16-point DIFs (even / odd rows) per thread, packed ---------------
-            {
-                const uint32_t* st = t >= tiles1 ? st_c1 : st_c0;
-                pk_t re[16], im[16];
-                auto unpack = [&](auto swapped) {
-                    constexpr uint32_t sel_lo = 0x7610u, sel_hi = 0x7632u;
-                    constexpr uint32_t sel_i = decltype(swapped)::value ? sel_hi : sel_lo;
-                    constexpr uint32_t sel_q = decltype(swapped)::value ? sel_lo : sel_hi;
-                    uint32_t ex = exp_seed;
-#pragma unroll
-                    for (int m1 = 0; m1 < 16; ++m1) {
-                        const int row = 32 * m1 + 2 * m2p1;
-                        const uint32_t w0 = st[row * 4] ^ xmask, w1 = st[(row + 1) * 4] ^ xmask;
-                        const uint32_t i0 = __byte_perm(w0, ex, sel_i), i1 = __byte_perm(w1, ex, sel_i);
-                        const uint32_t q0 = __byte_perm(w0, ex, sel_q), q1 = __byte_perm(w1, ex, sel_q);
-                        ex = i0;
-                        re[m1] = pk_add(pk_make_u(i0, i1), bias_i);
-                        im[m1] = pk_add(pk_make_u(q0, q1), bias_q);
-                    }
-                };
-                if (p.iq_swap) unpack(std::true_type{});
-                else unpack(std::false_type{});
-                // this warp's rows are in registers: the last of the 8 warps to get here starts the next tile's copy
-                __syncwarp();
-                if ((tid & 31) == 0 && (atomicAdd(&s_ctl[0], 1) & 7) == 7 && t + 1 < ntiles) issue(t + 1);
-                pk_dif<16>(re, im);
-                const uint32_t dst = smem_u32(T) + (m2p1 * RS + slot) * 16;
-                static_for<16>([&](auto kc) {
-                    constexpr int k1 = decltype(kc)::value;
-                    if constexpr (k1 != 0) {
-                        // W_256^{m2 k1}: an 8-byte load that the two row groups of a warp share; ptxas turns the
-                        // (w, w) pairs into scalar-broadcast operands of the packed ops
-                        const pk_t xr = re[bitrev<16>(k1)], xi = im[bitrev<16>(k1)];
-                        const float2 w = tw256[k1 * 16 + m2p1];
-                        const pk_t wr = pk_make(w.x, w.x), wi = pk_make(w.y, w.y);
-                        re[bitrev<16>(k1)] = pk_sub(pk_mul(xr, wr), pk_mul(xi, wi));
-                        im[bitrev<16>(k1)] = pk_fma(xr, wi, pk_mul(xi, wr));
-                    }
-                });
-                __syncthreads();       // the tile is free: every warp has left the previous multiply-accumulate
-                static_for<16>([&](auto kc) {
-                    constexpr int k1 = decltype(kc)::value;
-                    sts64_at<16 * (k1 * 16) * RS>(dst, re[bitrev<16>(k1)]);
-                    sts64_at<16 * (k1 * 16) * RS + 8>(dst, im[bitrev<16>(k1)]);
-                });
-            }
+            // ------------- pass 1 (rows -> registers -> 16-point DIFs -> tile), pass 2 (in place) ----------------------
+            pass1_5(t >= tiles1 ? st_c1 : st_c0, m2p1, slot, T, tw256, unpack,
+                    [&] {
+                        // this warp's rows are in registers: the last of the 8 warps to get here starts the next copy
+                        __syncwarp();
+                        if ((tid & 31) == 0 && (atomicAdd(&s_ctl[0], 1) & 7) == 7 && t + 1 < ntiles)
+                            issue_tile5(stage, bar, maps, geo, p, tmap_row0, blk0, t + 1);
+                    },
+                    [&] { __syncthreads(); });   // the tile is free: every warp has left the previous multiply-accumulate
             __syncthreads();
-            // ------------- pass 2: 16-point DIF over m2, in place ----------------------------------------
-            {
-                const int k1 = rg;
-                const uint32_t colp = smem_u32(T) + ((k1 * 16) * RS + slot) * 16;
-                pk_t re[16], im[16];
-                static_for<16>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    const ulonglong2 v = lds128_at<16 * i * RS>(colp);
-                    re[i] = v.x;
-                    im[i] = v.y;
-                });
-                pk_dif<16>(re, im);
-                static_for<16>([&](auto kc) {
-                    constexpr int k2 = decltype(kc)::value;
-                    sts64_at<16 * k2 * RS>(colp, re[bitrev<16>(k2)]);
-                    sts64_at<16 * k2 * RS + 8>(colp, im[bitrev<16>(k2)]);
-                });
-            }
+            pass2_5(T, rg, slot);
             // table entry q of this tile: per (entry, c, r) one float4 (a_k', a_k'+256, b_k', b_k'+256)
             auto gload = [&](float4 (&g)[CG], int e) {
 #pragma unroll
@@ -383,26 +436,26 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             const bool chain_end = t + 1 == tiles1 || t + 1 == ntiles;
 #ifdef IQ2A_G3SETS
             gload(g2, t * 4 + 2);
-            pair_mac(0, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
-            pair_mac(1, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
             gload(g0, t * 4 + 3);
-            pair_mac(0, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
-            pair_mac(1, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
             if (chain_end) gload(g1, ntiles * 4 + (t + 1 == ntiles ? 1 : 0));
-            pair_mac(0, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g2);
-            pair_mac(1, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g2);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g2);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g2);
             float4 (&g_orph)[CG] = g0;
             float4 (&g_end)[CG] = g1;
 #else
             // two table-entry register sets, each reloaded as soon as its step is done (one step ahead)
-            pair_mac(0, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
-            pair_mac(1, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 1>(trow), lds128_at<16 * 7>(trow), g0);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 9>(trow), lds128_at<16 * 15>(trow), g0);
             gload(g0, t * 4 + 2);
-            pair_mac(0, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
-            pair_mac(1, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 2>(trow), lds128_at<16 * 6>(trow), g1);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 10>(trow), lds128_at<16 * 14>(trow), g1);
             gload(g1, t * 4 + 3);
-            pair_mac(0, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g0);
-            pair_mac(1, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g0);
+            pair_mac5<CG, BT>(acc, 0, wc, lds128_at<16 * 3>(trow), lds128_at<16 * 5>(trow), g0);
+            pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 11>(trow), lds128_at<16 * 13>(trow), g0);
             if (chain_end) gload(g0, ntiles * 4 + (t + 1 == ntiles ? 1 : 0));
             float4 (&g_orph)[CG] = g1;
             float4 (&g_end)[CG] = g0;
@@ -412,25 +465,12 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                 const ulonglong2 c0 = chain_start ? zero : lds128_at<0>(orow);
                 const ulonglong2 c1 = chain_start ? zero : lds128_at<4096>(orow);
                 const ulonglong2 m0 = lds128_at<16 * 4>(trow), m1 = lds128_at<16 * 12>(trow);
-                pair_mac(0, lds128_at<0>(trow), c0, g_orph);
-                pair_mac(1, lds128_at<16 * 8>(trow), c1, g_orph);
+                pair_mac5<CG, BT>(acc, 0, wc, lds128_at<0>(trow), c0, g_orph);
+                pair_mac5<CG, BT>(acc, 1, wc, lds128_at<16 * 8>(trow), c1, g_orph);
                 if (chain_end) {
-                    // the column left over at the end of a class is its own mirror: plain complex product with
-                    // the entry (e.re, e.im) packed like a pair entry
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) {
-                        pk_t xr, xi;
-                        radix2(b ? m1.x : m0.x, b ? m1.y : m0.y, xr, xi);
-                        const pk_t nxi = xi ^ 0x8000000080000000ull;
-#pragma unroll
-                        for (int c = 0; c < CG; ++c) {
-                            const pk_t er = pk_make(g_end[c].x, g_end[c].y), ei = pk_make(g_end[c].z, g_end[c].w);
-                            acc[0][c][b] = pk_fma(er, xr, acc[0][c][b]);
-                            acc[0][c][b] = pk_fma(ei, nxi, acc[0][c][b]);
-                            acc[1][c][b] = pk_fma(er, xi, acc[1][c][b]);
-                            acc[1][c][b] = pk_fma(ei, xr, acc[1][c][b]);
-                        }
-                    }
+                    // the column left over at the end of a class is its own mirror: plain complex product
+                    single_mac5<CG, BT>(acc, 0, wc, m0, g_end);
+                    single_mac5<CG, BT>(acc, 1, wc, m1, g_end);
                 } else {
                     // carry the spectrum of mirror column 0 to the next tile (own rows only: no barrier needed)
                     asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(orow), "l"(m0.x), "l"(m0.y) : "memory");

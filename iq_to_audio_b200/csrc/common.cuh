@@ -56,6 +56,26 @@ struct PairGeo {
     int dm[2], hw[2], hl[2];   // per class: mirror row offset, rows of the wrap box, rows of a linear box
 };
 
+// Many-channel (split) form of the mirror-pair kernel (channelizer5s.cuh)
+struct SplitGroup {
+    int first, count;         // channels [first, first + count) of the bank
+    size_t g5_off;            // float4 offset of the group's table in the bank's pair table
+};
+
+struct SplitParams {
+    float4* scratch;          // [sets_in_wave][ntiles][16][256]
+    int set0;                 // first block set of the wave
+    int nsets;                // block sets in the wave
+    int tiles_per_cta;        // k_forward5: consecutive tiles one CTA transforms
+    const SplitGroup* groups; // device
+    const float4* gtab5;      // the bank's pair table
+    const double* w;          // [C] signed NCO increments (device)
+    const double* phase_bias; // [C] (device)
+    const float2* rot;        // [C][ld]
+    const double* phase_tab;  // [C][nseg]
+    float2* out;              // [C][out_stride]
+};
+
 // table entries of the mirror-pair kernel per channel: 4 per tile + the column left at the end of each class
 inline int pair_table_entries(const PairGeo& g) { return 4 * g.ntiles + 2; }
 

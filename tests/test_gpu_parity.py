@@ -346,6 +346,36 @@ def test_pipelined_stream_equals_synchronous_chunks(gpu):
         np.testing.assert_allclose(a[3], b[3], rtol=0, atol=1e-9)   # float64 atomics: summation order varies
 
 
+def test_many_channel_form_equals_fused_kernel(gpu, monkeypatch):
+    """25+ channels of one filter take the many-channel form (csrc/channelizer5s.cuh: forward transforms once per
+    wave of block sets, then a multiply-accumulate kernel per group of <= 4 channels).  Same arithmetic in the same
+    order as the fused kernel: identical channel samples, ragged calls included."""
+    fs, d = 10e6, 104
+    taps = orc.channel_taps(fs, 12_500.0, d)
+    rng = np.random.default_rng(29)
+    n = 900_011
+    raw = rng.integers(-20_000, 20_000, 2 * n, dtype=np.int16)
+    T = gpu["Target"]
+    tg = [T((-4.7 + 0.35 * i) * 1e6, taps, 1 if i % 3 else -1, "iq") for i in range(27)]
+    sizes = [400_000, 7, 300_000, n]
+
+    def run():
+        with gpu["ChannelBank"](fs, d, tg, ref_chunk=1 << 18, fft_size=512) as bank:
+            pos, parts, launches = 0, [], bank.launches
+            for sz in sizes:
+                e = min(n, pos + sz)
+                if e > pos:
+                    parts.append(bank.process_chunk(raw[2 * pos:2 * e], want_baseband=True).baseband.copy())
+                pos = e
+            return np.concatenate(parts, axis=1), bank.launches - launches
+    many, l_many = run()
+    monkeypatch.setenv("IQ2A_MANY", "0")
+    fused, l_fused = run()
+    assert many.shape == fused.shape == (27, orc.decimated_count(0, n, d))
+    assert np.array_equal(many, fused)
+    assert l_many != l_fused                                       # the two forms really are different launch sequences
+
+
 def test_batched_stream_keeps_reference_chunk_semantics(gpu):
     """ChannelBank.stream(..., chunk_frames=): several reference chunks per GPU call.  Phase wraps, AGC restarts and
     DecoderStats stay per reference chunk, so the result equals the one-chunk-per-call run (the block grid of the
