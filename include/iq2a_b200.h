@@ -84,7 +84,8 @@ typedef struct iq2a_bank_info {
     int64_t hop;             /* Ld * D input samples per block      */
     int64_t halo;            /* input samples of history a segment start needs (Vd * D) */
     double  fs_channel;
-    int32_t kernel_generation; /* 2: TMA + packed-f32x2 channel-bank kernel in use, 1: first-generation only */
+    int32_t kernel_generation; /* 5: mirror-pair kernel (symmetric taps), 4: TMA / cp.async + packed-f32x2 kernel, 1: first
+                                  generation only, 0: direct mode (D = 1..2: float64 mixer + direct-form filter) */
     int32_t reserved;
 } iq2a_bank_info;
 

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = CSRC / "_obj"
 LIB = PKG / "libiq2a_b200.so"
-SOURCES = ["cabi.cu", "channelizer.cu", "channelizer5s_inst.cu", "tail.cu", "stage.cu", "precise.cu", "resample.cu", "spectrum.cu"]
+SOURCES = ["cabi.cu", "channelizer.cu", "channelizer5s_inst.cu", "tail.cu", "stage.cu", "precise.cu", "precise_fft.cu", "resample.cu", "spectrum.cu"]
 FFT_SIZES = (512, 1024)
 GROUP_SIZES = (1, 2, 3, 4, 5, 6)
 NVCC_FLAGS = [

@@ -139,6 +139,11 @@ struct iq2a_bank {
     int* d_setctr = nullptr;        // block-set counter of the generation-5 kernel (dynamic scheduling)
     // many-channel form (channelizer5s.cuh): forward transforms once per wave of block sets, groups of <= 4 channels
     bool many_ok = false;
+    // low-rate captures (D = 1..2 with 1025+ taps: more history rows than any transform size holds): every channel's
+    // samples come from the float64 mixer + direct-form filter of the bit-faithful path; `exact` lists the channels
+    // computed that way (direct mode: all, otherwise the SSB+AGC ones)
+    bool direct_mode = false;
+    std::vector<int> exact;
     SplitGroup* d_split_groups = nullptr;
     double* d_phase_bias = nullptr;
     float4* d_scratch = nullptr;    size_t scratch_cap = 0;
@@ -379,7 +384,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     }
     if (b->timing) IQ2A_CUDA_TRY(cudaEventRecord(b->ev[1], a.st));
     // ---- head fix-up: stream start rows recomputed in float64 ----------------------------
-    if (a.mg_begin < b->vd) {
+    if (a.mg_begin < b->vd && !b->direct_mode) {
         const int64_t last = std::min<int64_t>(a.mg_end, b->vd);
         HeadParams h{};
         h.raw = a.d_raw;
@@ -404,11 +409,11 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         b->launches++;
     }
     // ---- bit-faithful channel samples for SSB+AGC channels (precise.cu) ------------------------
-    if (!b->precise.empty()) {
+    if (!b->exact.empty()) {
         const int D = b->D, Q = b->vd - 1;
         const int64_t batch = std::max<int64_t>(1024, (24LL << 20) / D) & ~(int64_t)31;
-        for (size_t pi = 0; pi < b->precise.size(); ++pi) {
-            const int c = b->precise[pi];
+        for (size_t pi = 0; pi < b->exact.size(); ++pi) {
+            const int c = b->exact[pi];
             for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
                 const int64_t r1 = std::min(n_rows, r0 + batch);
                 const int64_t rows_pad = (r1 - r0 + 31) & ~(int64_t)31;
@@ -440,7 +445,9 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
                 if ((rc = dev_grow(&b->d_mixed, &b->mixed_cap, (size_t)m.count))) return rc;
                 m.mixed = b->d_mixed;
                 if ((rc = launch_mix_exact(m, b->cfg.codec, a.st))) return rc;
-                if (pi < b->fir_plans.size() && b->fir_plans[pi].M > 0)
+                if (pi < b->fir_plans.size() && b->fir_plans[pi].M > 0 && b->fir_plans[pi].reg)
+                    rc = launch_fir_fft64r(b->fir_plans[pi], b->d_mixed, r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st);
+                else if (pi < b->fir_plans.size() && b->fir_plans[pi].M > 0)
                     rc = launch_fir_fft64(b->fir_plans[pi], b->d_mixed, r1 - r0, b->d_bb + (size_t)c * stride + r0, a.st);
                 else
                     rc = launch_fir_decim_f64(b->d_mixed, b->d_taps + b->tap_off[c], (int)b->taps[c].size(), D, Q,
@@ -604,6 +611,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     const int D = cfg->decimation;
     const int vd = (nt_max - 1 + D - 1) / D + 1;      // plan.py: overlap_rows
     int M = cfg->fft_size;
+    bool direct = false;
     if (M == 0) {
         // cost per new sample ~ (5 log2 M + 8 C') / (1 - vd/M); 1024 only when it clearly wins -- and never for int16
         // input whose filter fits 512: the TMA / packed-f32x2 kernels (generations 4, 5) exist for M = 512 only and
@@ -613,10 +621,12 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         M = (cost(1024) < 0.95 * cost(512)) ? 1024 : 512;
         const char* env = std::getenv("IQ2A_CHANNELIZER");
         if (cfg->codec == IQ2A_CODEC_S16 && vd + 16 < 512 && !(env && std::strcmp(env, "v1") == 0)) M = 512;
-        if (cost(M) >= 1e300) { set_error("channel filter too long for the supported transform sizes (%d history rows)", vd); return IQ2A_ERR_INVALID; }
+        // no transform size holds the history (sample rates up to ~2 x fs_ch: D = 1..2 with the 1025+ taps the reference
+        // always designs): direct mode.  The reference handles every rate (OverlapSaveFIR has no such limit).
+        if (cost(M) >= 1e300) { direct = true; M = 512; }
     }
     if (M != 512 && M != 1024) { set_error("fft_size must be 512 or 1024"); return IQ2A_ERR_INVALID; }
-    if (vd + 16 >= M) { set_error("channel filter too long for fft_size %d (%d history rows)", M, vd); return IQ2A_ERR_INVALID; }
+    if (!direct && vd + 16 >= M) { set_error("channel filter too long for fft_size %d (%d history rows)", M, vd); return IQ2A_ERR_INVALID; }
 
     iq2a_bank* b = new (std::nothrow) iq2a_bank();
     if (!b) { set_error("out of host memory"); return IQ2A_ERR_NOMEM; }
@@ -626,7 +636,8 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     b->M = M;
     b->R1 = 32;
     b->vd = vd;
-    b->ld = M - vd;
+    b->ld = direct ? 256 : M - vd;
+    b->direct_mode = direct;
     int rc = IQ2A_OK;
     auto fail = [&](int code) { delete b; return code; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", cfg->device); return fail(IQ2A_ERR_CUDA); }
@@ -665,7 +676,8 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             const bool off = env && std::strcmp(env, "0") == 0;
             const size_t qp = (size_t)((vd - 1 + 8) & ~7);            // k_fir_decim_f64: 128 rows + padded history, 16 lanes
             const size_t fir_smem = (128 + qp) * 16 * 16 + qp * 16 * 8;
-            if (!off && fir_smem <= 200 * 1024) {
+            (void)fir_smem;                                           // longer histories take k_fir_rows_f64
+            if (!off) {
                 tc[c].precise = 1;
                 b->precise.push_back(c);
             } else {
@@ -676,6 +688,8 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         tn[c] = ch[c].ntaps;
         all_taps.insert(all_taps.end(), b->taps[c].begin(), b->taps[c].end());
     }
+    if (direct) for (int c = 0; c < C; ++c) b->exact.push_back(c);
+    else b->exact = b->precise;
     // channel groups: runs of consecutive channels with the same filter length on the same path (fast / bit-faithful),
     // each run in groups of <= gmax channels -- so that a group can take the mirror-pair kernel with its own geometry
     // and a group of bit-faithful channels is not computed twice; too many runs: plain groups of consecutive channels
@@ -700,6 +714,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
             else runs.push_back({c, 1});
         }
         if ((int)runs.size() > 8) runs.assign(1, {0, C});
+        if (direct) runs.clear();
         for (const auto& run : runs) {
             const int ng = (run.second + gmax - 1) / gmax;
             for (int g = 0, first = run.first; g < ng; ++g) {
@@ -725,7 +740,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         twf[t] = make_float2((float)wtab[t].x, (float)wtab[t].y);
     }
     double2* d_wtab = nullptr;
-    if ((rc = dev_alloc(&b->d_gtab, g_total)) || (rc = dev_alloc(&b->d_tw, (size_t)M)) ||
+    if ((rc = dev_alloc(&b->d_gtab, std::max<size_t>(g_total, 1))) || (rc = dev_alloc(&b->d_tw, (size_t)M)) ||
         (rc = dev_alloc(&b->d_taps, all_taps.size())) || (rc = dev_alloc(&b->d_tap_off, (size_t)C)) ||
         (rc = dev_alloc(&b->d_ntaps, (size_t)C)) || (rc = dev_alloc(&b->d_w, (size_t)C)) ||
         (rc = dev_alloc(&b->d_chan, (size_t)C)) || (rc = dev_alloc(&b->d_state, (size_t)C)) ||
@@ -743,15 +758,22 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         if ((rc = dev_alloc(&b->d_precise, b->precise.size())) || (rc = dev_alloc(&b->d_repaired, (size_t)1))) { cudaFree(d_wtab); return fail(rc); }
         ok &= cudaMemcpy(b->d_precise, b->precise.data(), b->precise.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(b->d_repaired, 0, sizeof(int)) == cudaSuccess;
-        // "fft": the transform form of the float64 filter (1.4x faster end to end on cfg3's shape, but 1.3e-4 of its
-        // samples round to the neighbouring complex64 -- the polyphase sum cancels ~80 dB of out-of-band signal in
-        // float64 -- and the point of this path is that they do not; the direct form is the default)
+    }
+    if (!b->exact.empty()) {
+        // float64 channel filter of these channels: "direct" = precise.cu's direct form (2 * ntaps DFMAs per sample),
+        // "fft" = its first transform form (1.3e-4 of the samples round to the neighbouring complex64), default = the
+        // register-pass transform form with repair of every sample near a rounding boundary (precise_fft.cu): the
+        // direct form's result, bit for bit, at a fraction of its cost
         const char* env = std::getenv("IQ2A_PRECISE_FIR");
-        if (env && std::strcmp(env, "fft") == 0) {
-            b->fir_plans.resize(b->precise.size());
-            for (size_t pi = 0; pi < b->precise.size(); ++pi) {
-                const int c = b->precise[pi];
-                if ((rc = fir_fft_plan_create(&b->fir_plans[pi], b->d_taps + toff[c], tn[c], D, vd - 1, b->stream))) { cudaFree(d_wtab); return fail(rc); }
+        const bool want_direct = env && std::strcmp(env, "direct") == 0;
+        const bool want_old_fft = env && std::strcmp(env, "fft") == 0;
+        if (!want_direct) {
+            b->fir_plans.resize(b->exact.size());
+            for (size_t pi = 0; pi < b->exact.size(); ++pi) {
+                const int c = b->exact[pi];
+                rc = want_old_fft ? fir_fft_plan_create(&b->fir_plans[pi], b->d_taps + toff[c], tn[c], D, vd - 1, b->stream)
+                                  : fir_fftr_plan_create(&b->fir_plans[pi], b->d_taps + toff[c], tn[c], D, vd - 1, b->stream);
+                if (rc) { cudaFree(d_wtab); return fail(rc); }
                 b->launches += 2;
             }
         }
@@ -797,7 +819,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
                 b->pair_ok = true;
             }
         }
-        b->kernel_gen = b->pair_ok ? 5 : ((b->v2_ok || b->cp_ok) ? 4 : 1);
+        b->kernel_gen = direct ? 0 : (b->pair_ok ? 5 : ((b->v2_ok || b->cp_ok) ? 4 : 1));
         b->many_ok = many;
         for (const Group& g : b->groups) b->many_ok = b->many_ok && g.pair_ok;
         if (b->many_ok) {

@@ -155,12 +155,34 @@ k_fir_decim_f64(const float2* __restrict__ mixed, const double* __restrict__ tap
     }
 }
 
+// The same sum with one thread per output row (taps in ascending order): for the low-rate captures whose history does
+// not fit the tiled kernel -- a 144 kS/s capture is 144 k rows x 1025 taps per second of signal.
+__global__ void __launch_bounds__(128) k_fir_rows_f64(const float2* __restrict__ mixed, const double* __restrict__ taps,
+                                                      int ntaps, int D, int Q, int64_t nrows, float2* __restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nrows) return;
+    const float2* x = mixed + (m + Q) * (int64_t)D;          // the sample that meets h[0]; `mixed` row 0 is output row -Q
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k < ntaps; ++k) {
+        const float2 v = x[-k];
+        const double h = __ldg(taps + k);
+        ar = fma(h, (double)v.x, ar);
+        ai = fma(h, (double)v.y, ai);
+    }
+    out[m] = make_float2((float)ar, (float)ai);
+}
+
 int launch_fir_decim_f64(const float2* d_mixed, const double* d_taps, int ntaps, int D, int Q, int64_t nrows,
                          float2* d_out, cudaStream_t st) {
     if (nrows <= 0) return IQ2A_OK;
     const int Qp = (Q + kFirTile) & ~(kFirTile - 1);
     const size_t smem = (size_t)(kFirRows + Qp) * kFirLanes * sizeof(double2) + (size_t)Qp * kFirLanes * sizeof(double);
-    if (smem > 220 * 1024) { set_error("channel filter too long for the bit-faithful path (%d history rows)", Q); return IQ2A_ERR_INVALID; }
+    if (smem > 220 * 1024) {
+        // more history rows than the tiled kernel's shared memory holds (D = 1..2): one thread per output row
+        k_fir_rows_f64<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(d_mixed, d_taps, ntaps, D, Q, nrows, d_out);
+        IQ2A_CUDA_TRY(cudaGetLastError());
+        return IQ2A_OK;
+    }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         IQ2A_CUDA_TRY(cudaFuncSetAttribute(k_fir_decim_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -278,6 +300,8 @@ int fir_fft_plan_create(FirFftPlan* pl, const double* d_taps, int ntaps, int D, 
 void fir_fft_plan_destroy(FirFftPlan* pl) {
     if (pl->H) cudaFree(pl->H);
     if (pl->tw) cudaFree(pl->tw);
+    if (pl->risky) cudaFree(pl->risky);
+    if (pl->n_risky) cudaFree(pl->n_risky);
     *pl = FirFftPlan{};
 }
 

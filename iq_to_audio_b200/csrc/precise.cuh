@@ -63,11 +63,23 @@ int launch_seq_tail(const SeqParams& p, cudaStream_t st, int64_t* launches);
 // signal, M-point float64 transforms): ~20x fewer operations than the direct form, same rounding to complex64.
 struct FirFftPlan {
     int M = 0, Q = 0, D = 0;
-    double2* H = nullptr;      // [D][M] branch filter spectra / M, natural bin order (device)
+    double2* H = nullptr;      // [D][M] branch filter spectra / M (device); natural bin order, or row order (reg = true)
     double2* tw = nullptr;     // [M] exp(-2 pi i k / M) (device)
+    // register-pass form with repair (precise_fft.cu)
+    bool reg = false;
+    int ntaps = 0;
+    const double* taps = nullptr;   // device, owned by the bank
+    int* risky = nullptr;           // rows to recompute by the direct form
+    size_t risky_cap = 0;
+    int* n_risky = nullptr;         // [0]: entries of `risky` in the current launch, [1]: total repaired so far
+    double tol = 1e-12;             // distance to a float32 rounding boundary below which a sample is recomputed
 };
 int fir_fft_plan_create(FirFftPlan* plan, const double* d_taps, int ntaps, int D, int Q, cudaStream_t st);
 void fir_fft_plan_destroy(FirFftPlan* plan);
 int launch_fir_fft64(const FirFftPlan& plan, const float2* d_mixed, int64_t nrows, float2* d_out, cudaStream_t st);
+// register-pass transform form + repair of every sample near a float32 rounding boundary (precise_fft.cu): the
+// direct form's result at ~1/15 of its cost
+int fir_fftr_plan_create(FirFftPlan* plan, const double* d_taps, int ntaps, int D, int Q, cudaStream_t st);
+int launch_fir_fft64r(FirFftPlan& plan, const float2* d_mixed, int64_t nrows, float2* d_out, cudaStream_t st);
 
 }  // namespace iq2a

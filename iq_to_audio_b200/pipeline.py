@@ -22,6 +22,7 @@ from __future__ import annotations
 import logging
 import math
 import os
+import sys
 import queue
 import re
 import shutil
@@ -158,7 +159,7 @@ class IQReader:
     RING_DEPTH = 3
 
     def __init__(self, path: Path, chunk_size: int, iq_order: str, input_format: InputFormat, *,
-                 sample_rate: float | None = None, pinned: bool = False, batch: int = 1):
+                 sample_rate: float | None = None, pinned: bool = False, batch: int = 1, device: int = 0):
         if iq_order not in _lib.ORDER_IDS:
             raise ValueError(f"Unsupported iq_order '{iq_order}'")
         self.path = Path(path)
@@ -169,6 +170,7 @@ class IQReader:
         self.input_bytes_per_frame = input_format.bytes_per_frame
         self.batch = max(1, int(batch))          # reference chunks per read_raw_block(batched=True)
         self.pinned = bool(pinned)
+        self.device = int(device)
         self._fh = None
         self._ring: list[np.ndarray] = []
         self._ring_ptrs: list[int] = []
@@ -237,7 +239,7 @@ class IQReader:
             n = raw.size // self.input_bytes_per_frame
             out = np.empty(n, dtype=np.complex64)
             _lib.check(lib.iq2a_unpack_mix(raw.ctypes.data, n, codec_id, _lib.ORDER_IDS[self.iq_order], 0.0, 0.0,
-                                           out.ctypes.data, 0))
+                                           out.ctypes.data, self.device))
             yield out
 
 
@@ -261,7 +263,7 @@ class AudioWriter:
     rate (no resampling) and says so -- the 48 kHz libswresample-exact stage is the next row of the
     scope table, not part of this one."""
 
-    def __init__(self, output_path: Path, input_rate: float, *, require_ffmpeg: bool = False):
+    def __init__(self, output_path: Path, input_rate: float, *, require_ffmpeg: bool = False, device: int = 0):
         self.output_path = Path(output_path)
         self.input_rate = float(input_rate)
         self.ffmpeg_rate = max(1, int(round(self.input_rate)))
@@ -282,13 +284,15 @@ class AudioWriter:
                 self.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stderr=subprocess.PIPE)
             except OSError as exc:
                 raise RuntimeError(f"Failed to launch ffmpeg: {exc}") from exc
-            self._queue: queue.SimpleQueue = queue.SimpleQueue()
+            # bounded: the GPU produces audio orders of magnitude faster than ffmpeg takes it, so an unbounded queue
+            # would hold the whole backlog in host memory; a full queue back-pressures the producer instead
+            self._queue: queue.Queue = queue.Queue(maxsize=64)
             self._thread = threading.Thread(target=self._drain, name="AudioWriter", daemon=True)
             self._thread.start()
         else:
             from .resample import Resampler48k
             LOG.info("Encoding natively: %d Hz float32 -> 48 kHz PCM_16 on the GPU.", self.ffmpeg_rate)
-            self._res = Resampler48k(self.ffmpeg_rate, 1) if self.ffmpeg_rate > 48_000 else None
+            self._res = Resampler48k(self.ffmpeg_rate, 1, device=device) if self.ffmpeg_rate > 48_000 else None
             if self._res is None and self.ffmpeg_rate != 48_000:
                 raise RuntimeError(f"channel rate {self.ffmpeg_rate} Hz is below 48 kHz: ffmpeg is required to upsample")
             self._wav = wave.open(str(self.output_path), "wb")
@@ -322,7 +326,14 @@ class AudioWriter:
         if safe.size == 0:
             return
         if self.proc is not None:
-            self._queue.put(np.ascontiguousarray(safe, dtype=np.float32).tobytes())
+            payload = np.ascontiguousarray(safe, dtype=np.float32).tobytes()
+            while True:
+                try:
+                    self._queue.put(payload, timeout=1.0)
+                    break
+                except queue.Full:
+                    if self._error or not self._thread.is_alive():
+                        raise RuntimeError("ffmpeg writer failed") from self._error
         elif self._res is not None:
             self._wav.writeframes(self._res.process(safe)[0].astype("<i2").tobytes())
         else:   # already 48 kHz: swr's flt -> s16 conversion only
@@ -334,14 +345,21 @@ class AudioWriter:
             return
         self._closed = True
         if self.proc is not None:
-            self._queue.put(None)
-            self._thread.join(timeout=30)
+            # the drain thread must have written everything before stdin closes: wait for it as long as it makes
+            # progress (it ends on the sentinel, or on a pipe error that is surfaced below)
+            while self._thread.is_alive():
+                try:
+                    self._queue.put(None, timeout=1.0)
+                    break
+                except queue.Full:
+                    continue
+            self._thread.join()
             try:
                 self.proc.stdin.close()
             except OSError:
                 pass
             try:
-                self.proc.wait(timeout=10)
+                self.proc.wait(timeout=60)
             except subprocess.TimeoutExpired:
                 self.proc.terminate()
             if self._error:
@@ -554,6 +572,7 @@ class ProcessingPipeline:
             center = found.value
             cfg.center_freq, cfg.center_freq_source = center, found.source
 
+        targets = [f if f > 0 else center for f in targets]      # probe-only without --ft: the centre itself (:880-881)
         decimation, fs_channel = channel_decimation(sample_rate, cfg.fs_ch_target)       # :885-890
         chunk = tune_chunk_size(sample_rate, cfg.chunk_size)                            # :929
         max_samples = None
@@ -589,7 +608,7 @@ class ProcessingPipeline:
                 from .numa import bind_to_device_numa
                 LOG.debug("host placement: %s", bind_to_device_numa(cfg.device))
             with IQReader(Path(cfg.in_path), chunk, cfg.iq_order, fmt, sample_rate=sample_rate, pinned=True,
-                          batch=batch) as reader:
+                          batch=batch, device=cfg.device) as reader:
                 self._check_cancel("initialization")
                 first = reader.read_raw_block(max_samples)
                 if first is None:
@@ -604,7 +623,7 @@ class ProcessingPipeline:
                     warm = np.empty(nfr, dtype=np.complex64)
                     _lib.check(lib.iq2a_unpack_mix(first.ctypes.data, nfr, _lib.CODEC_IDS[fmt.codec],
                                                    _lib.ORDER_IDS[cfg.iq_order], 0.0, 0.0, warm.ctypes.data, cfg.device))
-                    signs = [choose_mix_sign(warm, sample_rate, f - center, taps, decimation) for f in targets]
+                    signs = [choose_mix_sign(warm, sample_rate, f - center, taps, decimation, device=cfg.device) for f in targets]
                 LOG.info("Selected mixer sign(s) %s based on warm-up snippet.", signs)
                 self._check_cancel("warm-up")
                 if cfg.probe_only:
@@ -619,7 +638,7 @@ class ProcessingPipeline:
                 if pass_through:                                   # processing.py:1014-1015
                     writers = [IQSliceWriter(o, fs_channel, fmt) for o in outputs]
                 else:
-                    writers = [AudioWriter(o, fs_channel) for o in outputs]
+                    writers = [AudioWriter(o, fs_channel, device=cfg.device) for o in outputs]
                 if cfg.dump_iq_path:                               # one cf32 dump per target (cli.py:623, :666)
                     dumps = [self._annotate(Path(cfg.dump_iq_path), f, len(targets)).open("wb") for f in targets]
                 want_bb = pass_through or bool(dumps)
@@ -680,8 +699,15 @@ class ProcessingPipeline:
                     LOG.debug("Failed to remove cancelled output %s", o)
             raise
         finally:
+            # every writer and dump is closed even if one close() raises; the first failure is re-raised
+            failure = None
             for w in writers:
-                w.close()
+                try:
+                    w.close()
+                except Exception as exc:                      # noqa: BLE001
+                    failure = failure or exc
             for fd in dumps:
                 fd.close()
             prog.close()
+            if failure is not None and sys.exc_info()[0] is None:
+                raise failure

@@ -144,7 +144,7 @@ class Decimator:
 
 
 def choose_mix_sign(warmup: np.ndarray, sample_rate: float, freq_offset: float, taps: np.ndarray,
-                    decimation: int) -> int:
+                    decimation: int, *, device: int | None = None) -> int:
     """Pick the mixer sign that leaves more power in the channel (ref: processing.py:623-663).
 
     Both candidate signs are run as two channels of one bank over the warm-up snippet; the
@@ -161,7 +161,7 @@ def choose_mix_sign(warmup: np.ndarray, sample_rate: float, freq_offset: float, 
     d = max(decimation, 1)
     cands = (1, -1)
     with ChannelBank(sample_rate, d, [Target(freq_offset, taps, s, "iq") for s in cands],
-                     codec="complex64", ref_chunk=max(take, 1), device=_DEVICE) as bank:
+                     codec="complex64", ref_chunk=max(take, 1), device=_DEVICE if device is None else int(device)) as bank:
         bb = bank.process_chunk(snippet, want_baseband=True).baseband
     best_sign, best_power = 1, -np.inf
     for row, sign in zip(bb, cands):

@@ -346,6 +346,40 @@ def test_pipelined_stream_equals_synchronous_chunks(gpu):
         np.testing.assert_allclose(a[3], b[3], rtol=0, atol=1e-9)   # float64 atomics: summation order varies
 
 
+@pytest.mark.parametrize("fs,mode", [(120_000.0, "nfm"), (96_000.0, "am"), (130_000.0, "usb")])
+def test_low_rate_capture_direct_mode(gpu, fs, mode):
+    """Sample rates up to ~1.5 x fs_ch give D = 1 and, with the 1025+ taps the reference always designs, more history
+    rows than any transform size holds.  The reference handles every rate (OverlapSaveFIR has no limit;
+    Decimator(1) returns its input, processing.py:354-356); the bank switches to direct mode -- the float64 mixer and
+    direct-form filter of the bit-faithful path for every channel -- instead of rejecting the capture."""
+    d, fs_ch = orc.plan_decimation(fs, 96_000.0)
+    assert d == 1
+    n = 150_003
+    kind = {"nfm": "fm", "am": "am", "usb": "usb"}[mode]
+    off = 0.17 * fs
+    car = dict(offset=off, amp=0.3, kind=kind, tone=800.0)
+    if kind == "fm":
+        car["dev"] = 2500.0
+    raw = orc.to_s16(orc.multi_carrier_capture(fs, n, [car], noise_std=0.01, seed=3))
+    bw = 12_500.0 if mode == "nfm" else 6_000.0
+    taps = orc.channel_taps(fs, bw, d)
+    assert len(taps) >= 1025
+    chunk = 1 << 16
+    T = gpu["Target"]
+    with gpu["ChannelBank"](fs, d, [T(off, taps, 1, mode, 300.0, True)], ref_chunk=chunk) as bank:
+        assert bank.kernel_generation == 0
+        parts = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, n)], want_baseband=True) for s in range(0, n, chunk)]
+    bb = np.concatenate([p.baseband for p in parts], axis=1)[0]
+    clipped = np.concatenate([p.clipped for p in parts], axis=1)[0]
+    x = orc.order_iq(orc.unpack_interleaved(raw, "pcm_s16le"), "iq")
+    plan = orc.TargetPlan(sample_rate=fs, freq_offset=off, bandwidth=bw, mode=mode, agc_enabled=True, mix_sign=1)
+    want = orc.run_target(x, plan, chunk)
+    assert bb.size == want.baseband.size == n
+    assert np.mean(bb == want.baseband) > 0.9999                   # float64 direct sum vs the reference's complex128 FFT
+    assert np.abs(bb - want.baseband).max() <= BB_TOL
+    assert np.abs(clipped - want.clipped).max() <= AUDIO_TOL
+
+
 def test_many_channel_form_equals_fused_kernel(gpu, monkeypatch):
     """25+ channels of one filter take the many-channel form (csrc/channelizer5s.cuh: forward transforms once per
     wave of block sets, then a multiply-accumulate kernel per group of <= 4 channels).  Same arithmetic in the same
@@ -712,11 +746,13 @@ def test_edge_inputs_empty_tiny_and_sub_row_calls(gpu):
         assert np.abs(r.audio[0] - want.audio).max() <= AUDIO_TOL
 
 
-def test_bit_faithful_filter_transform_form_vs_direct_form(gpu, monkeypatch):
-    """The float64 channel filter of the bit-faithful path exists as a direct form (default) and as a transform form
-    (IQ2A_PRECISE_FIR=fft, ~20x fewer operations).  The direct form reproduces the reference's complex64 channel
-    samples; the transform form cancels ~80 dB of out-of-band signal in its polyphase sum and lands on the
-    neighbouring float32 for about one sample in 10^4 -- close, but not what this path is for."""
+def test_bit_faithful_filter_forms(gpu, monkeypatch):
+    """The float64 channel filter of the bit-faithful path in its three forms.  Direct form (IQ2A_PRECISE_FIR=direct,
+    2 * ntaps DFMAs per sample): reproduces the reference's complex64 channel samples.  Register-pass transform form
+    with repair (default, csrc/precise_fft.cu): every sample within 1e-12 of a float32 rounding boundary is
+    recomputed by the direct sum, so the result is the direct form's, bit for bit.  First transform form
+    (IQ2A_PRECISE_FIR=fft): cancels ~80 dB of out-of-band signal in its polyphase sum and lands on the neighbouring
+    float32 for about one sample in 10^4 -- close, but not what this path is for."""
     names = ["case_c_20M_usb", "case_c_20M_lsb"]
     m, fs, d, tg_all, gold_all = _targets(gpu, "case_c_20M_am_ssb", ["case_c_20M_am"] + names)
     raw = _cases.raw_input("case_c_20M_am_ssb")
@@ -727,11 +763,14 @@ def test_bit_faithful_filter_transform_form_vs_direct_form(gpu, monkeypatch):
             parts = [bank.process_chunk(raw[2 * s:2 * min(s + chunk, raw.size // 2)], want_baseband=True)
                      for s in range(0, raw.size // 2, chunk)]
             return np.concatenate([p.baseband for p in parts], axis=1), np.concatenate([p.clipped for p in parts], axis=1)
+    bb_reg, clip_reg = run()
+    monkeypatch.setenv("IQ2A_PRECISE_FIR", "direct")
     bb_dir, clip_dir = run()
     monkeypatch.setenv("IQ2A_PRECISE_FIR", "fft")
     bb_fft, clip_fft = run()
     for i, g in enumerate(gold_all[1:]):
         assert np.mean(bb_dir[i] == g["baseband"]) > 0.99999
         assert np.abs(clip_dir[i] - g["clipped"]).max() <= AUDIO_TOL
+        assert np.array_equal(bb_reg[i], bb_dir[i]) and np.array_equal(clip_reg[i], clip_dir[i])
         assert np.mean(bb_fft[i] == bb_dir[i]) > 0.999
         assert np.abs(bb_fft[i] - bb_dir[i]).max() <= 1e-7
