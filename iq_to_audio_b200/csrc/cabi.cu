@@ -411,7 +411,12 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
     // ---- bit-faithful channel samples for SSB+AGC channels (precise.cu) ------------------------
     if (!b->exact.empty()) {
         const int D = b->D, Q = b->vd - 1;
-        const int64_t batch = std::max<int64_t>(1024, (24LL << 20) / D) & ~(int64_t)31;
+        // rows per pass: ~300 blocks of the transform-form filter (two CTAs per SM), i.e. 0.5 GB of mixed samples
+        // rows per pass: one round of the transform-form filter's CTAs (two per SM, 1024 - Q rows each) when it is in
+        // use -- a second, mostly empty round costs as much as a full one -- else ~0.5 GB of mixed samples
+        int64_t batch = std::max<int64_t>(1024, (64LL << 20) / D) & ~(int64_t)31;
+        if (!b->fir_plans.empty() && b->fir_plans[0].reg && b->fir_plans[0].M > 0)
+            batch = (int64_t)2 * b->n_sm_total * (b->fir_plans[0].M - Q);
         for (size_t pi = 0; pi < b->exact.size(); ++pi) {
             const int c = b->exact[pi];
             for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {

@@ -41,7 +41,9 @@ struct Geo5 {
     static constexpr int NT = 256, RS = 17;
     static constexpr size_t tile_bytes = (size_t)256 * RS * 16;
     static constexpr size_t orph_bytes = 2 * 256 * 16;           // carried spectrum: [block][row] (E.re, O.re, E.im, O.im)
-    static constexpr size_t smem = tile_bytes + 4 * (size_t)kRegionBytes + orph_bytes + 256 * sizeof(float2) + 32;
+    // (the mbarrier, the two control words and the epilogue's 12 block phasors live in the first 16 entries of the
+    // twiddle table, which belong to k1 = 0 and are never read: 2 x (smem + 1 KB reserved) is exactly the 228 KB of an SM)
+    static constexpr size_t smem = tile_bytes + 4 * (size_t)kRegionBytes + orph_bytes + 512 * sizeof(float2);
 };
 
 // ---- pieces shared by the fused kernel (k_channelize5) and the split kernels (channelizer5s.cuh) ----------------
@@ -229,12 +231,12 @@ __device__ __forceinline__ void single_mac5(pk_t (&acc)[2][CG][BT], int b, float
 // output rows 2 rho and 2 rho + 1.  The rotation table entries a thread needs are fixed (rho = thread index), so
 // they are requested before the passes and have landed when the store needs them.
 template <int CG>
-__device__ __forceinline__ void inverse_store5(float4* Y, const float2* tw256, const ChannelizeParams& p, int blk0,
-                                               pk_t (&acc)[2][CG][2], float2 wc, int tid) {
+__device__ __forceinline__ void inverse_store5(float4* Y, const float2* tw256, float2* s_base, const ChannelizeParams& p,
+                                               int blk0, pk_t (&acc)[2][CG][2], float2 wc, int tid) {
     constexpr int BT = 2, NS = CG * BT, YS4 = NS + 1, NT = Geo5::NT;
     static_assert((size_t)(256 * YS4 + 16) * 16 <= Geo5::tile_bytes && 16 * NS <= NT, "layout");
     auto yaddr = [&](int rho, int sy) { return smem_u32(Y) + (uint32_t)(rho * YS4 + (rho >> 4) + sy) * 16; };
-    __shared__ float2 s_base[kMaxGroup * 2];
+    // (s_base: CG x 2 block phasors, in the caller's shared memory -- the kernel has no static allocation to spare)
     // ---- radix-2 step on the accumulators, spectra -> shared ------------------------------------------------
     {
         const uint32_t dst = yaddr(tid, 0);
@@ -349,7 +351,8 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     unsigned char* stage = smem_raw + Geo5::tile_bytes;
     unsigned char* orph = stage + 4 * kRegionBytes;
     float2* tw256 = reinterpret_cast<float2*>(orph + Geo5::orph_bytes);      // [k1][m2] = W_256^{m2 k1} = W_512^{2 m2 k1}
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tw256 + 256);
+    float2* wctab = tw256 + 256;                              // [r] = W_512^{k'(r)}: the last radix-2 stage's twiddle of row r
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw256);       // entries 0..15 (k1 = 0) of the table are never read
     int* s_ctl = reinterpret_cast<int*>(bar + 1);             // [0]: 8 x tiles taken out of the staging buffer (+ warps of the current one), [1]: next block set
 
     const int tid = threadIdx.x;
@@ -357,7 +360,8 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     const int b_slot = slot >> 3, side = (slot >> 2) & 1, col = slot & 3;
     const int m2p1 = (rg + 2 * b_slot) & 15;           // pass-1 row group of this thread (see header: banks)
 
-    tw256[tid] = p.twid[2 * (((tid & 15) * (tid >> 4)) & 255)];
+    if (tid >= 16) tw256[tid] = p.twid[2 * (((tid & 15) * (tid >> 4)) & 255)];
+    wctab[tid] = p.twid[(tid >> 4) + 16 * (tid & 15)];
     if (tid == 0) {
         mbar_init(bar, 1);
         s_ctl[0] = 0;
@@ -368,7 +372,6 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
 
     const int r_mac = tid;
     const int kq = (r_mac >> 4) + 16 * (r_mac & 15);          // bin within the 256-point halves
-    const float2 wc = p.twid[kq];                             // W_512^{k'}
     const float4* __restrict__ gtab = reinterpret_cast<const float4*>(p.gtab) + r_mac;
     const uint32_t orow = smem_u32(orph) + r_mac * 16;        // this thread's carried spectrum (block b: + b * 4096)
 
@@ -432,6 +435,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             // slots of block b: forward columns b*8 + 0..3, mirror columns b*8 + 4..7; column i pairs with
             // mirror column 4 - i (i = 1, 2, 3); forward column 0 pairs with the carried spectrum
             const uint32_t trow = smem_u32(T) + r_mac * RS * 16;
+            const float2 wc = wctab[tid];                            // W_512^{k'}: not kept in registers through the passes
             const bool chain_start = t == 0 || t == tiles1;
             const bool chain_end = t + 1 == tiles1 || t + 1 == ntiles;
 #ifdef IQ2A_G3SETS
@@ -483,7 +487,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
         // next block set: a global counter when the launch provides one (CTAs run at different speeds: the L2 slice
         // an SM is close to, the other CTA on the SM), the static stride otherwise
         if (tid == 0) s_ctl[1] = p.set_counter ? (int)gridDim.x + atomicAdd(p.set_counter, 1) : set + (int)gridDim.x;
-        inverse_store5<CG>(T, tw256, p, blk0, acc, wc, tid);
+        inverse_store5<CG>(T, tw256, tw256 + 2, p, blk0, acc, wctab[tid], tid);
         __syncthreads();
         set = s_ctl[1];
     }
@@ -493,10 +497,16 @@ template <int CG>
 static int launch_channelize5_cg(const ChannelizeParams& p, const PairMaps& maps, const PairGeo& geo, int64_t tmap_row0,
                                  int n_sm, cudaStream_t st) {
     auto kern = k_channelize5<CG>;
-    static bool configured = false;
-    if (!configured) {
+    static int occ = 0;
+    if (!occ) {
         IQ2A_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo5::smem));
-        configured = true;
+        // the shared-memory budget is exact (Geo5::smem): make sure the two CTAs per SM the design counts on really fit
+        IQ2A_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Geo5::NT, Geo5::smem));
+        if (occ < 2) {
+            set_error("k_channelize5<%d>: %d CTA per SM fits (2 expected) -- shared memory or registers grew", CG, occ);
+            occ = 0;
+            return IQ2A_ERR_STATE;
+        }
     }
     const int nsets = (p.nblocks + 1) / 2;
     const int slots = n_sm * 2;                             // persistent: two CTAs per SM

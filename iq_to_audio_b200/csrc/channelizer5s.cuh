@@ -88,7 +88,7 @@ k_mac5(const ChannelizeParams base, const PairGeo geo, const SplitParams sp) {
     float4* T = reinterpret_cast<float4*>(smem_raw);                                  // epilogue workspace
     float2* tw256 = reinterpret_cast<float2*>(smem_raw + Geo5::tile_bytes);
     const int tid = threadIdx.x;
-    tw256[tid] = base.twid[2 * (((tid & 15) * (tid >> 4)) & 255)];
+    if (tid >= 16) tw256[tid] = base.twid[2 * (((tid & 15) * (tid >> 4)) & 255)];     // entries 0..15: the epilogue's phasors
 
     const SplitGroup grp = sp.groups[blockIdx.y];
     const int set_l = blockIdx.x;
@@ -177,7 +177,7 @@ k_mac5(const ChannelizeParams base, const PairGeo geo, const SplitParams sp) {
         p.phase_bias[c] = c < cnt ? sp.phase_bias[grp.first + c] : 0.0;
     }
     __syncthreads();                                       // tw256 is in place
-    inverse_store5<CG>(T, tw256, p, blk0, acc, wc, tid);
+    inverse_store5<CG>(T, tw256, tw256 + 2, p, blk0, acc, wc, tid);
 }
 
 struct Geo5M {

@@ -358,32 +358,50 @@ constexpr int kSeqWarm = 8192;
 __device__ __forceinline__ void dc_rows_warp(const float* __restrict__ x, float* __restrict__ y_out, int64_t a, int64_t b,
                                              float& x1, float& y1) {
     const int lane = threadIdx.x & 31;
-    for (int64_t base = a; base < b; base += 32) {
-        const int64_t r = base + lane;
-        const int cnt = (int)min((int64_t)32, b - base);
-        const float xv = r < b ? x[r] : 0.f;
-        float xprev = __shfl_up_sync(0xffffffffu, xv, 1);
-        if (lane == 0) xprev = x1;
-        const float diff = __fsub_rn(xv, xprev);
-        float mine = 0.f;
-        if (cnt == 32) {
-            // full group: the 32 shuffles do not depend on the carried value, so with the loop unrolled they are all
-            // in flight before the chain of 32 x (FMUL, FADD) starts -- the chain is what remains (8 cycles per row)
+    // the rows of the next kAhead groups are requested before the dependent chain of the current group runs: the chain
+    // (32 x (FMUL, FADD), ~260 cycles) is shorter than a load from HBM, so one group of look-ahead is not enough
+    constexpr int kAhead = 4;
+    float nxt[kAhead];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dj = __shfl_sync(0xffffffffu, diff, j);
-                y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
-                if (lane == j) mine = y1;
+    for (int i = 0; i < kAhead; ++i) {
+        const int64_t r = a + 32 * i + lane;
+        nxt[i] = r < b ? x[r] : 0.f;
+    }
+    for (int64_t base = a; base < b; base += 32 * kAhead) {
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) {
+            const int64_t gbase = base + 32 * i;
+            if (gbase >= b) break;
+            const int64_t r = gbase + lane;
+            const int cnt = (int)min((int64_t)32, b - gbase);
+            const float xv = nxt[i];
+            {
+                const int64_t rn = gbase + 32 * kAhead + lane;
+                nxt[i] = rn < b ? x[rn] : 0.f;
             }
-        } else {
-            for (int j = 0; j < cnt; ++j) {
-                const float dj = __shfl_sync(0xffffffffu, diff, j);
-                y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
-                if (lane == j) mine = y1;
+            float xprev = __shfl_up_sync(0xffffffffu, xv, 1);
+            if (lane == 0) xprev = x1;
+            const float diff = __fsub_rn(xv, xprev);
+            float mine = 0.f;
+            if (cnt == 32) {
+                // full group: the 32 shuffles do not depend on the carried value, so with the loop unrolled they are
+                // all in flight before the chain of 32 x (FMUL, FADD) starts -- the chain is what remains
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float dj = __shfl_sync(0xffffffffu, diff, j);
+                    y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
+                    if (lane == j) mine = y1;
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    const float dj = __shfl_sync(0xffffffffu, diff, j);
+                    y1 = __fadd_rn(dj, __fmul_rn(0.995f, y1));
+                    if (lane == j) mine = y1;
+                }
             }
+            if (y_out && r < b) y_out[r] = mine;
+            x1 = __shfl_sync(0xffffffffu, xv, cnt - 1);
         }
-        if (y_out && r < b) y_out[r] = mine;
-        x1 = __shfl_sync(0xffffffffu, xv, cnt - 1);
     }
 }
 
@@ -472,37 +490,56 @@ __global__ void __launch_bounds__(32) k_seq_agc(const SeqParams p) {
     float gain = 1.0f;                                                   // restarts every call (ssb.py:72)
     float peak = 0.f;
     double ss = 0.0;
-    for (int64_t base = rec.lo; base < rec.hi; base += 32) {
-        const int64_t r = base + lane;
-        const int cnt = (int)min((int64_t)32, rec.hi - base);
-        const float sv = r < rec.hi ? x[r] : 0.f;
-        const float mag = fabsf(sv);
-        const bool live = r < rec.hi && mag > 1e-6f;
-        const float desired = live ? __fdiv_rn(target, mag) : 0.f;
-        const unsigned mask = __ballot_sync(0xffffffffu, live);
-        float mine = 1.0f;
-        if (cnt == 32) {
+    constexpr int kAhead = 4;                                            // groups of 32 rows requested ahead (see dc_rows_warp)
+    float nxt[kAhead];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dj = __shfl_sync(0xffffffffu, desired, j);
-                const float g2 = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
-                gain = (mask & (1u << j)) ? g2 : gain;
-                if (lane == j) mine = gain;
+    for (int i = 0; i < kAhead; ++i) {
+        const int64_t r = rec.lo + 32 * i + lane;
+        nxt[i] = r < rec.hi ? x[r] : 0.f;
+    }
+    for (int64_t base0 = rec.lo; base0 < rec.hi; base0 += 32 * kAhead) {
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) {
+            const int64_t base = base0 + 32 * i;
+            if (base >= rec.hi) break;
+            const int64_t r = base + lane;
+            const int cnt = (int)min((int64_t)32, rec.hi - base);
+            const float sv = nxt[i];
+            {
+                const int64_t rn = base + 32 * kAhead + lane;
+                nxt[i] = rn < rec.hi ? x[rn] : 0.f;
             }
-        } else {
-            for (int j = 0; j < cnt; ++j) {
-                const float dj = __shfl_sync(0xffffffffu, desired, j);
-                if (mask & (1u << j)) gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
-                if (lane == j) mine = gain;
+            const float mag = fabsf(sv);
+            const bool live = r < rec.hi && mag > 1e-6f;
+            const float desired = live ? __fdiv_rn(target, mag) : 0.f;
+            // a row below the floor leaves the gain alone (ssb.py:75-76): with a zero step factor the update
+            // gain + 0 * (desired - gain) is exactly that, and the factor does not wait for the carried gain
+            const float step = live ? decay : 0.f;
+            const unsigned mask = __ballot_sync(0xffffffffu, live);
+            float mine = 1.0f;
+            if (cnt == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float dj = __shfl_sync(0xffffffffu, desired, j);
+                    const float sj = __shfl_sync(0xffffffffu, step, j);
+                    gain = __fadd_rn(gain, __fmul_rn(sj, __fsub_rn(dj, gain)));
+                    if (lane == j) mine = gain;
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    const float dj = __shfl_sync(0xffffffffu, desired, j);
+                    if (mask & (1u << j)) gain = __fadd_rn(gain, __fmul_rn(decay, __fsub_rn(dj, gain)));
+                    if (lane == j) mine = gain;
+                }
             }
+            if (r >= rec.hi || r < p.n_skip) continue;
+            const float o = __fmul_rn(sv, mine);
+            const int64_t oi = r - p.n_skip;
+            if (p.audio) p.audio[(size_t)c * p.out_stride + oi] = o;
+            if (p.clipped) p.clipped[(size_t)c * p.out_stride + oi] = fminf(fmaxf(o, -0.99f), 0.99f);
+            peak = fmaxf(peak, fabsf(o));
+            ss = fma((double)o, (double)o, ss);
         }
-        if (r >= rec.hi || r < p.n_skip) continue;
-        const float o = __fmul_rn(sv, mine);
-        const int64_t oi = r - p.n_skip;
-        if (p.audio) p.audio[(size_t)c * p.out_stride + oi] = o;
-        if (p.clipped) p.clipped[(size_t)c * p.out_stride + oi] = fminf(fmaxf(o, -0.99f), 0.99f);
-        peak = fmaxf(peak, fabsf(o));
-        ss = fma((double)o, (double)o, ss);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -8,13 +8,15 @@
 // ~80 dB of out-of-band signal and the float64 rounding error of the transforms is no longer negligible against a
 // float32 half-ulp.  This file fixes both:
 //   k_fir_fft64r   M = 1024 = 32 x 32: each 1024-point transform is two passes of 32-point DIFs held in registers
-//                  (two shared-memory round trips), 8 branch columns per tile, branch spectra H in row order so the
+//                  (two shared-memory round trips), 4 branch columns per tile and 128 threads so that two CTAs share
+//                  an SM (one loads while the other transforms), branch spectra H in row order so the
 //                  multiply-accumulate reads it coalesced.  Every output whose float64 value lies within `tol` of the
 //                  midpoint between two float32 values is appended to a repair list.
 //   k_fir_repair   one CTA per listed sample: the float64 direct form over all taps (the sum precise.cu computes),
-//                  rounded once.  ~0.3 % of the samples at the default tolerance.
-// A sample that is NOT listed is at least `tol` = 1e-12 away from any rounding boundary, two orders of magnitude
-// more than the transform's error (~1e-14 for |x| <= 1), so its float32 rounding is the direct form's.
+//                  rounded once.  4 tol / ulp(|s|) of the samples: 1e-5 at |s| ~ 0.1, 0.4 % for a channel 50 dB down.
+// A sample that is NOT listed is at least `tol` = 3e-14 away from any rounding boundary, ~30x the transform's error
+// (measured: tools/precise_tol_sweep.py), so its float32 rounding is the direct form's.
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -27,9 +29,10 @@ namespace iq2a {
 namespace {
 
 constexpr int kM = 1024;
-constexpr int kCols = 8;                   // branch columns per tile
+constexpr int kCols = 4;                   // branch columns per tile
 constexpr int kRS = kCols + 1;             // tile row stride (double2): conflict-free column reads by consecutive rows
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;              // kCols x 32 row groups; 248 registers each -> two CTAs per SM
+constexpr int kBins = kM / kThreads;       // spectrum rows per thread in the multiply-accumulate
 constexpr size_t kTileBytes = (size_t)kM * kRS * sizeof(double2);
 constexpr size_t kSmem = kTileBytes + (size_t)kM * sizeof(double2);
 
@@ -72,7 +75,7 @@ __device__ __forceinline__ void ddif(double2 (&v)[32], const double2* __restrict
 // In-place forward 1024-point transforms of `ncol` columns of the tile (element n of column c at s[n*kRS + c]).
 // X[k] ends up in row (k & 31) * 32 + (k >> 5).
 __device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restrict__ tw, int ncol) {
-    const int c = threadIdx.x & (kCols - 1), g = threadIdx.x >> 3;          // g: 0..31
+    const int c = threadIdx.x & (kCols - 1), g = threadIdx.x / kCols;        // g: 0..31
     double2 v[32];
     if (c < ncol) {
         // pass 1: n = m2 + 32 m1, 32-point DIF over m1 for m2 = g, then W_1024^{m2 k1}; result k1 -> row k1*32 + m2
@@ -129,7 +132,7 @@ __device__ __forceinline__ double boundary_distance(double v) {
     return fabs(v - mid);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, const double2* __restrict__ tw_g, int D, int Q,
              int64_t nrows, float2* __restrict__ out, double tol, int* __restrict__ risky, int* __restrict__ n_risky,
              int risky_cap) {
@@ -140,9 +143,9 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
     const int ld = kM - Q;
     const int64_t row0 = (int64_t)blockIdx.x * ld;                         // first `mixed` row of this block
     const int64_t src_rows = nrows + Q;
-    double2 acc[4];
+    double2 acc[kBins];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = make_double2(0.0, 0.0);
+    for (int i = 0; i < kBins; ++i) acc[i] = make_double2(0.0, 0.0);
     __syncthreads();
     for (int p0 = 0; p0 < D; p0 += kCols) {
         const int ncol = min(kCols, D - p0);
@@ -159,7 +162,7 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
         __syncthreads();
         fft1024_tile(s, tw, ncol);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kBins; ++i) {
             const int rho = threadIdx.x + i * kThreads;
             const double2* xs = s + (size_t)rho * kRS;
             const double2* hs = H + (size_t)p0 * kM + rho;
@@ -173,7 +176,7 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
     }
     // inverse transform: IFFT(Y) = conj(FFT(conj(Y))) (1/M is in H); Y[k] goes to row k (natural order) of column 0
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kBins; ++i) {
         const int rho = threadIdx.x + i * kThreads;
         const int k = (rho >> 5) + 32 * (rho & 31);
         s[(size_t)k * kRS] = make_double2(acc[i].x, -acc[i].y);
@@ -194,36 +197,55 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
     }
 }
 
-// float64 direct form for the listed rows: out[m] = c64( sum_k h[k] mixed[(m + Q) D - k] ), `mixed` row 0 = output row -Q
-__global__ void __launch_bounds__(256) k_fir_repair(const float2* __restrict__ mixed, const double* __restrict__ taps, int ntaps,
-                                                    int D, int Q, const int* __restrict__ risky, const int* __restrict__ n_risky,
+// float64 direct form for the listed rows: out[m] = c64( sum_k h[k] mixed[(m + Q) D - k] ), `mixed` row 0 = output row -Q.
+// A CTA of 1024 threads takes kRepairBatch listed rows at a time (32 taps per thread and row): one tap load feeds
+// that many independent multiply-add chains and that many sample loads are in flight per thread -- a single row per
+// 256-thread CTA was bound by the latency of its own 128 dependent iterations.
+constexpr int kRepairBatch = 4;
+constexpr int kRepairThreads = 1024;
+
+__global__ void __launch_bounds__(kRepairThreads) k_fir_repair(const float2* __restrict__ mixed, const double* __restrict__ taps, int ntaps,
+                                                    int D, int Q, const int* __restrict__ risky, int* __restrict__ n_risky,
                                                     int risky_cap, float2* __restrict__ out) {
-    __shared__ double2 part[256];
+    __shared__ double2 part[kRepairBatch][kRepairThreads / 32];
     const int total = min(*n_risky, risky_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(const_cast<int*>(n_risky) + 1, total);
-    for (int it = blockIdx.x; it < total; it += gridDim.x) {
-        const int64_t m = risky[it];
-        const int64_t top = (m + Q) * (int64_t)D;                 // index into `mixed` of the sample that meets h[0]
-        double ar = 0.0, ai = 0.0;
-        for (int k = threadIdx.x; k < ntaps; k += 256) {
-            const int64_t i = top - k;
-            if (i >= 0) {
-                const float2 x = mixed[i];
-                const double h = taps[k];
-                ar = fma(h, (double)x.x, ar);
-                ai = fma(h, (double)x.y, ai);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_risky + 1, total);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int it = blockIdx.x * kRepairBatch; it < total; it += gridDim.x * kRepairBatch) {
+        const float2* top[kRepairBatch];                          // the sample that meets h[0]
+        int64_t mrow[kRepairBatch];
+#pragma unroll
+        for (int j = 0; j < kRepairBatch; ++j) {
+            mrow[j] = risky[min(it + j, total - 1)];
+            top[j] = mixed + (mrow[j] + Q) * (int64_t)D;
+        }
+        double ar[kRepairBatch], ai[kRepairBatch];
+#pragma unroll
+        for (int j = 0; j < kRepairBatch; ++j) ar[j] = ai[j] = 0.0;
+        for (int k = threadIdx.x; k < ntaps; k += kRepairThreads) {
+            const double h = __ldg(taps + k);
+#pragma unroll
+            for (int j = 0; j < kRepairBatch; ++j) {
+                const float2 x = __ldg(top[j] - k);
+                ar[j] = fma(h, (double)x.x, ar[j]);
+                ai[j] = fma(h, (double)x.y, ai[j]);
             }
         }
-        part[threadIdx.x] = make_double2(ar, ai);
+#pragma unroll
+        for (int j = 0; j < kRepairBatch; ++j) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ar[j] += __shfl_xor_sync(0xffffffffu, ar[j], off);
+                ai[j] += __shfl_xor_sync(0xffffffffu, ai[j], off);
+            }
+            if (lane == 0) part[j][warp] = make_double2(ar[j], ai[j]);
+        }
         __syncthreads();
-        for (int off = 128; off > 0; off >>= 1) {
-            if (threadIdx.x < off) {
-                part[threadIdx.x].x += part[threadIdx.x + off].x;
-                part[threadIdx.x].y += part[threadIdx.x + off].y;
-            }
-            __syncthreads();
+        if (threadIdx.x < kRepairBatch && it + threadIdx.x < total) {
+            double tr = 0.0, ti = 0.0;
+            for (int w = 0; w < kRepairThreads / 32; ++w) { tr += part[threadIdx.x][w].x; ti += part[threadIdx.x][w].y; }
+            out[mrow[threadIdx.x]] = make_float2((float)tr, (float)ti);
         }
-        if (threadIdx.x == 0) out[m] = make_float2((float)part[0].x, (float)part[0].y);
         __syncthreads();
     }
 }
@@ -239,6 +261,7 @@ int fir_fftr_plan_create(FirFftPlan* pl, const double* d_taps, int ntaps, int D,
     pl->ntaps = ntaps;
     pl->taps = d_taps;
     pl->reg = true;
+    if (const char* env = std::getenv("IQ2A_PRECISE_TOL")) pl->tol = std::atof(env);
     IQ2A_CUDA_TRY(cudaMalloc(&pl->tw, (size_t)kM * sizeof(double2)));
     IQ2A_CUDA_TRY(cudaMalloc(&pl->H, (size_t)D * kM * sizeof(double2)));
     IQ2A_CUDA_TRY(cudaMalloc(&pl->n_risky, 2 * sizeof(int)));
@@ -271,7 +294,7 @@ int launch_fir_fft64r(FirFftPlan& pl, const float2* d_mixed, int64_t nrows, floa
     const unsigned grid = (unsigned)((nrows + ld - 1) / ld);
     k_fir_fft64r<<<grid, kThreads, kSmem, st>>>(d_mixed, pl.H, pl.tw, pl.D, pl.Q, nrows, d_out, pl.tol, pl.risky, pl.n_risky,
                                                 (int)pl.risky_cap);
-    k_fir_repair<<<592, 256, 0, st>>>(d_mixed, pl.taps, pl.ntaps, pl.D, pl.Q, pl.risky, pl.n_risky, (int)pl.risky_cap, d_out);
+    k_fir_repair<<<592, kRepairThreads, 0, st>>>(d_mixed, pl.taps, pl.ntaps, pl.D, pl.Q, pl.risky, pl.n_risky, (int)pl.risky_cap, d_out);
     IQ2A_CUDA_TRY(cudaGetLastError());
     return IQ2A_OK;
 }

@@ -377,7 +377,14 @@ def test_low_rate_capture_direct_mode(gpu, fs, mode):
     assert bb.size == want.baseband.size == n
     assert np.mean(bb == want.baseband) > 0.9999                   # float64 direct sum vs the reference's complex128 FFT
     assert np.abs(bb - want.baseband).max() <= BB_TOL
-    assert np.abs(clipped - want.clipped).max() <= AUDIO_TOL
+    skip = 0
+    if mode == "nfm" and abs(want.baseband[0]) < 1e-12:
+        # h[0] of this filter is ~1e-20 (the window edge falls on a zero of the sinc), so the reference's s[0] is pure
+        # transform round-off (|s[0]| ~ 1e-16 where the exact value is 4e-21) and its first discriminator output the
+        # angle of that noise; the de-emphasis recurrence carries the arbitrary value for ~100 rows (0.97^n)
+        assert abs(bb[0]) < 1e-18
+        skip = 400
+    assert np.abs(clipped[skip:] - want.clipped[skip:]).max() <= AUDIO_TOL
 
 
 def test_many_channel_form_equals_fused_kernel(gpu, monkeypatch):
