@@ -383,6 +383,12 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     const uint32_t* const st_c0 = st_base + (side ? geo.dm[0] : geo.dm[0] + 1) * 4;
     const uint32_t* const st_c1 = st_base + (side ? geo.dm[1] : geo.dm[1] + 1) * 4;
 
+    // The copy of a tile is issued by ONE thread: the first tile of a set by thread 0 as soon as the set is known (for
+    // every set but a CTA's first: before the epilogue of the set before, which does not touch the staging buffer),
+    // the others by lane 0 of the last warp that has taken its rows out of the staging buffer (a counter in shared
+    // memory) -- as early as the buffer is free, half a pass before the barrier that every warp waits at.
+    if (tid == 0 && (int)blockIdx.x < nsets) issue_tile5(stage, bar, maps, geo, p, tmap_row0, blockIdx.x * BT, 0);
+
     for (int set = blockIdx.x; set < nsets;) {
         const int blk0 = set * BT;
         // acc[0][c][b] = (re_k', re_k'+256), acc[1][c][b] = (im_k', im_k'+256)
@@ -393,11 +399,6 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
             for (int c = 0; c < CG; ++c)
 #pragma unroll
                 for (int b = 0; b < BT; ++b) acc[h][c][b] = 0ull;
-
-        // The copy of a tile is issued by ONE thread: at the start of a set thread 0, inside the loop lane 0 of the
-        // last warp that has taken its rows out of the staging buffer (a counter in shared memory) -- as early as the
-        // buffer is free, half a pass before the barrier that every warp waits at.
-        if (tid == 0) issue_tile5(stage, bar, maps, geo, p, tmap_row0, blk0, 0);
 
         for (int t = 0; t < ntiles; ++t) {
             // every warp bumps s_ctl[0] once per tile after the wait below, so the tile's sequence number -- and with
@@ -486,7 +487,11 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
 
         // next block set: a global counter when the launch provides one (CTAs run at different speeds: the L2 slice
         // an SM is close to, the other CTA on the SM), the static stride otherwise
-        if (tid == 0) s_ctl[1] = p.set_counter ? (int)gridDim.x + atomicAdd(p.set_counter, 1) : set + (int)gridDim.x;
+        if (tid == 0) {
+            const int next = p.set_counter ? (int)gridDim.x + atomicAdd(p.set_counter, 1) : set + (int)gridDim.x;
+            s_ctl[1] = next;
+            if (next < nsets) issue_tile5(stage, bar, maps, geo, p, tmap_row0, next * BT, 0);
+        }
         inverse_store5<CG>(T, tw256, tw256 + 2, p, blk0, acc, wctab[tid], tid);
         __syncthreads();
         set = s_ctl[1];
