@@ -354,6 +354,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     float2* wctab = tw256 + 256;                              // [r] = W_512^{k'(r)}: the last radix-2 stage's twiddle of row r
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw256);       // entries 0..15 (k1 = 0) of the table are never read
     int* s_ctl = reinterpret_cast<int*>(bar + 1);             // [0]: 8 x tiles taken out of the staging buffer (+ warps of the current one), [1]: next block set
+    uint64_t* bar_free = reinterpret_cast<uint64_t*>(tw256 + 14);   // "every warp has left the tile": 8 arrivals per tile
 
     const int tid = threadIdx.x;
     const int slot = tid & 15, rg = tid >> 4;
@@ -364,6 +365,7 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
     wctab[tid] = p.twid[(tid >> 4) + 16 * (tid & 15)];
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar_free, NT / 32);
         s_ctl[0] = 0;
     }
     __syncthreads();
@@ -403,6 +405,12 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
         for (int t = 0; t < ntiles; ++t) {
             // every warp bumps s_ctl[0] once per tile after the wait below, so the tile's sequence number -- and with
             // it the phase of the barrier -- is s_ctl[0] / 8 for every thread that gets here (no register spent on it)
+            // The tile may be overwritten when every warp is done reading it (the multiply-accumulate phase of the
+            // tile before, or the epilogue): a warp says so HERE, before its own pass-1 arithmetic, and waits for the
+            // others only when it is about to store -- a CTA barrier at the store would make every warp wait for the
+            // slowest warp's pass 1 as well.
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_free);
             mbar_wait(bar, ((uint32_t)*reinterpret_cast<volatile int*>(s_ctl) >> 3) & 1u);
             // ------------- pass 1 (rows -> registers -> 16-point DIFs -> tile), pass 2 (in place) ----------------------
             pass1_5(t >= tiles1 ? st_c1 : st_c0, m2p1, slot, T, tw256, unpack,
@@ -412,7 +420,8 @@ k_channelize5(const ChannelizeParams p, const __grid_constant__ PairMaps maps, c
                         if ((tid & 31) == 0 && (atomicAdd(&s_ctl[0], 1) & 7) == 7 && t + 1 < ntiles)
                             issue_tile5(stage, bar, maps, geo, p, tmap_row0, blk0, t + 1);
                     },
-                    [&] { __syncthreads(); });   // the tile is free: every warp has left the previous multiply-accumulate
+                    // (this warp has bumped s_ctl[0] for this tile: the tile's sequence number is (s_ctl[0] - 1) / 8)
+                    [&] { mbar_wait(bar_free, ((uint32_t)(*reinterpret_cast<volatile int*>(s_ctl) - 1) >> 3) & 1u); });
             __syncthreads();
             pass2_5(T, rg, slot);
             // table entry q of this tile: per (entry, c, r) one float4 (a_k', a_k'+256, b_k', b_k'+256)
