@@ -53,7 +53,7 @@ def workload_name(seconds: float) -> str:
 # ------------------------------------------------------------------------------------------
 # synthetic capture: 5 FM carriers + AWGN, int16 interleaved
 # ------------------------------------------------------------------------------------------
-def synth_capture_device(n0: int, n: int, device, seed: int, fs: float | None = None, carriers=None):
+def synth_capture_device(n0: int, n: int, device, seed: int, fs: float | None = None, carriers=None, noise: float = 0.02):
     """int16 [2*n] on `device` for global sample indices [n0, n0+n): carriers are functions of the
     global index (float64 phase), noise is seeded per call.  `carriers`: (offset_hz, kind, tone_hz, amplitude) with
     kind fm / am / usb / lsb; default: the five FM carriers of cfg2 at the module's FS."""
@@ -81,8 +81,8 @@ def synth_capture_device(n0: int, n: int, device, seed: int, fs: float | None = 
             ph = torch.remainder(ph, two_pi)
             re += env * torch.cos(ph)
             im += env * torch.sin(ph)
-        noise = torch.randn((m, 2), device=device, dtype=torch.float32, generator=gen) * 0.02
-        iq = torch.stack((re.float() + noise[:, 0], im.float() + noise[:, 1]), dim=1).clamp_(-0.999, 0.999)
+        awgn = torch.randn((m, 2), device=device, dtype=torch.float32, generator=gen) * noise
+        iq = torch.stack((re.float() + awgn[:, 0], im.float() + awgn[:, 1]), dim=1).clamp_(-0.999, 0.999)
         out[2 * s:2 * (s + m)] = torch.round(iq * 32767.0).to(torch.int16).reshape(-1)
     return out
 
@@ -337,7 +337,7 @@ def main() -> None:
     _divert_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=SECONDS, help="capture length per GPU (default 60 s)")
@@ -569,7 +569,13 @@ def main() -> None:
     bank.set_timing(True)
     launches0 = bank.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    sampler = ClockSampler(local_rank)               # NVML initialisation takes a rank-dependent time: not in the bracket
+    with sampler as clocks:
+        if world > 1:
+            # the bracket of the timed region: the ranks enter together (any skew here is charged to the early rank,
+            # which then waits for the others at the writers' barrier: 2.04-2.56 ms per rank with five steps)
+            dist.barrier()
+        torch.cuda.synchronize()
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -644,7 +650,27 @@ def main() -> None:
             dist.all_gather(every, t)
             e2e_rank_ms = [float(v.item()) for v in every]
             e2e_ms = max(e2e_rank_ms)
+        # what the host can feed: the same pinned buffer copied to the device by every rank at once, nothing else
+        # running (the ceiling of the e2e number on this box: PCIe link per GPU x what the host memory system sustains)
+        sink = torch.empty(1 << 27, dtype=torch.int16, device=dev)                    # 256 MiB
+        piece = host[:min(host.numel(), sink.numel())]
+        reps_c = 8
+        sink[:piece.numel()].copy_(piece, non_blocking=True)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(reps_c):
+            sink[:piece.numel()].copy_(piece, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_gbps = reps_c * piece.numel() * 2 / (time.perf_counter() - t0) / 1e9
+        copy_rank = [copy_gbps]
+        if world > 1:
+            t = torch.tensor([copy_gbps], dtype=torch.float64, device=dev)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            copy_rank = [float(v.item()) for v in every]
+        del sink
         e2e = {"value": world * n_seg / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(4 * n_seg),
+               "h2d_copy_only_GBps": [round(v, 2) for v in copy_rank],
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e2e_ms,
                "per_rank_h2d_GBps": [round(4 * n_seg / (m * 1e-3) / 1e9, 2) for m in e2e_rank_ms],
                "api": f"ChannelBank.stream(chunk_frames={chunk}): submit/collect of {batch} reference chunks per call, 2 calls in flight, pinned host input"}

@@ -72,10 +72,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = LIB_PATH
+    if os.environ.get("IQ2A_LIB"):           # development aid: A/B a kernel variant built by tools/build_variant.py
+        path = Path(os.environ["IQ2A_LIB"])
+        if not path.exists():
+            raise RuntimeError(f"IQ2A_LIB={path} does not exist")
+    elif not LIB_PATH.exists():
         from . import build as _build
         _build.build()
-    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib = C.CDLL(os.fspath(path))
     vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     fp = C.c_void_p          # float* passed as raw addresses (numpy .ctypes.data or device pointers)
     lib.iq2a_last_error.restype = C.c_char_p

@@ -74,6 +74,10 @@ __device__ __forceinline__ void issue_tile5(unsigned char* stage, uint64_t* bar,
     const int mir = 4 * ((cls ? geo.g1 + geo.g2 : geo.g1) - 1 - j);                // mirror group w
     const int dm = cls ? geo.dm[1] : geo.dm[0], hw = cls ? geo.hw[1] : geo.hw[0], hl = cls ? geo.hl[1] : geo.hl[0];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef IQ2A_EXPERIMENT_NO_COPY          // timing experiment only (garbage results): what the copies cost the SM
+    mbar_arrive(bar);
+    return;
+#endif
     mbar_expect_tx(bar, (uint32_t)(2 * (3 * kFwdBoxRows + hw + 2 * hl) * 16));
 #pragma unroll
     for (int b = 0; b < 2; ++b) {

@@ -41,12 +41,52 @@ def device_numa_node(index: int) -> int | None:
     return node if node >= 0 else None
 
 
+def device_cpu_affinity(index: int) -> set[int] | None:
+    """The CPUs NVML calls ideal for device `index` (the fallback when sysfs has no NUMA node for the PCI device,
+    as in some virtualised boxes); None when NVML cannot say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = max(os.cpu_count() or 1, 64)
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (ncpu + 63) // 64)
+    except Exception:
+        return None
+    cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+    return cpus or None
+
+
+def host_topology() -> dict:
+    """NUMA nodes the kernel exposes and the CPUs this process may use (for the logs next to a throughput figure)."""
+    try:
+        nodes = sorted(int(p.name[4:]) for p in Path("/sys/devices/system/node").glob("node[0-9]*"))
+    except OSError:
+        nodes = []
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        allowed = os.cpu_count() or 0
+    return {"numa_nodes": len(nodes), "cpus_allowed": allowed}
+
+
 def bind_to_device_numa(index: int) -> dict:
     """Restrict the calling process to the CPUs of the GPU's NUMA node (no-op when the topology is unknown, the node
     has no CPUs in this cgroup, or the platform has no sched_setaffinity).  Returns what was done, for the logs."""
     info = {"device": index, "numa_node": device_numa_node(index), "bound": False}
     node = info["numa_node"]
-    if node is None or not hasattr(os, "sched_setaffinity"):
+    info.update(host_topology())
+    if not hasattr(os, "sched_setaffinity"):
+        return info
+    if node is None:
+        # no node in sysfs: take NVML's ideal CPU set when it is a proper subset of what we may use
+        ideal = device_cpu_affinity(index)
+        try:
+            allowed = os.sched_getaffinity(0)
+            use = sorted((ideal or set()) & allowed)
+            if use and len(use) < len(allowed):
+                os.sched_setaffinity(0, use)
+                info.update(bound=True, cpus=len(use), method="nvml cpu affinity")
+        except OSError:
+            pass
         return info
     try:
         node_cpus = _parse_cpulist((Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text())
