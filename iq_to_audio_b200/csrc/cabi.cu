@@ -161,6 +161,7 @@ struct iq2a_bank {
     TailChan* d_chan = nullptr;
     iq2a_channel_state* d_state = nullptr;
     double* d_phase = nullptr;   size_t phase_cap = 0;
+    float2* d_head_mixed = nullptr; size_t head_mixed_cap = 0;   // stream-start fix-up: mixed samples [C][vd * D]
     float2* d_bb = nullptr;      size_t bb_cap = 0;
     float* d_pre = nullptr;      size_t pre_cap = 0;
     float* d_tmp = nullptr;      size_t tmp_cap = 0;
@@ -186,7 +187,7 @@ struct iq2a_bank {
 
     ~iq2a_bank() {
         cudaSetDevice(cfg.device);
-        void* ptrs[] = {d_split_groups, d_phase_bias, d_scratch, d_setctr, d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_bb,
+        void* ptrs[] = {d_split_groups, d_phase_bias, d_scratch, d_setctr, d_gtab5, d_rot, d_precise, d_mixed, d_rec, d_repaired, d_gtab, d_gtab2, d_tw, d_taps, d_tap_off, d_ntaps, d_w, d_chan, d_state, d_phase, d_head_mixed, d_bb,
                         d_pre, d_tmp, d_audio, d_clip, d_agg, d_sumsq, d_ring[0], d_ring[1]};
         for (void* q : ptrs)
             if (q) cudaFree(q);
@@ -405,6 +406,15 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         h.out = b->d_bb;
         h.out_stride = stride;
         h.out_mg0 = a.mg_begin;
+        // every row of a channel reads the same mixed samples: mix them once when there is enough work to matter
+        // (C x rows x taps) and the scratch stays small
+        const int64_t n_in = (last - 1) * (int64_t)b->D + 1;
+        if ((int64_t)C * (last - a.mg_begin) >= 64 && (size_t)C * (size_t)n_in * sizeof(float2) <= ((size_t)256 << 20)) {
+            if ((rc = dev_grow(&b->d_head_mixed, &b->head_mixed_cap, (size_t)C * (size_t)n_in))) return rc;
+            h.mixed = b->d_head_mixed;
+            h.mixed_stride = n_in;
+            b->launches++;
+        }
         if ((rc = launch_head_direct(h, b->cfg.codec, (int)(last - a.mg_begin), C, a.st))) return rc;
         b->launches++;
     }

@@ -155,6 +155,23 @@ int launch_decimate(const float2* d_x, int64_t start, int factor, int64_t n_out,
 // the way the reference defines them -- mixed[n] = c64(x[n]) * c64(exp(j phi(n))) in
 // complex64, y = sum_k h[k] mixed[n-k] in float64 -- one CTA per (row, channel).
 // ---------------------------------------------------------------------------------------
+// mixed[c][idx] for idx = 0 .. n_in-1 (global sample index), exactly as k_head_direct forms it
+template <int FMT>
+__global__ void __launch_bounds__(256) k_head_mix(const HeadParams p, int64_t n_in) {
+    using raw_t = typename RawT<FMT>::type;
+    const raw_t* rp = reinterpret_cast<const raw_t*>(p.raw);
+    const int c = blockIdx.y;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_in) return;
+    const int64_t f = idx - p.raw_n0;
+    float2 xv = make_float2(0.f, 0.f);
+    if (f >= 0 && f < p.raw_len) xv = raw_to_c64<FMT>(rp[f], p.iq_swap, p.q_neg);
+    const double ph = nco_phase(p.phase, c, p.w[c], idx);
+    double s, co;
+    sincos(ph, &s, &co);
+    p.mixed[(size_t)c * p.mixed_stride + idx] = cmul_np(xv, make_float2((float)co, (float)s));
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) k_head_direct(const HeadParams p) {
     using raw_t = typename RawT<FMT>::type;
@@ -166,6 +183,15 @@ __global__ void __launch_bounds__(256) k_head_direct(const HeadParams p) {
     const int ntaps = p.ntaps[c];
     const int64_t kmax = min((int64_t)ntaps - 1, n);    // x[n-k] with n-k >= 0
     double ar = 0.0, ai = 0.0;
+    if (p.mixed) {
+        const float2* __restrict__ mx = p.mixed + (size_t)c * p.mixed_stride;
+        for (int64_t k = threadIdx.x; k <= kmax; k += blockDim.x) {
+            const float2 mixed = mx[n - k];
+            const double h = taps[k];
+            ar = fma(h, (double)mixed.x, ar);
+            ai = fma(h, (double)mixed.y, ai);
+        }
+    } else
     for (int64_t k = threadIdx.x; k <= kmax; k += blockDim.x) {
         const int64_t idx = n - k;
         const int64_t f = idx - p.raw_n0;
@@ -197,6 +223,16 @@ __global__ void __launch_bounds__(256) k_head_direct(const HeadParams p) {
 int launch_head_direct(const HeadParams& p, int codec, int nrows, int nchan, cudaStream_t st) {
     if (nrows <= 0) return IQ2A_OK;
     const dim3 grid(nrows, nchan);
+    if (p.mixed) {
+        const int64_t n_in = (p.mg_begin + nrows - 1) * (int64_t)p.decim + 1;
+        const dim3 gm((unsigned)((n_in + 255) / 256), nchan);
+        switch (codec) {
+            case CODEC_S16: k_head_mix<CODEC_S16><<<gm, 256, 0, st>>>(p, n_in); break;
+            case CODEC_U8: k_head_mix<CODEC_U8><<<gm, 256, 0, st>>>(p, n_in); break;
+            case CODEC_F32: k_head_mix<CODEC_F32><<<gm, 256, 0, st>>>(p, n_in); break;
+            default: set_error("unknown codec %d", codec); return IQ2A_ERR_INVALID;
+        }
+    }
     switch (codec) {
         case CODEC_S16: k_head_direct<CODEC_S16><<<grid, 256, 0, st>>>(p); break;
         case CODEC_U8: k_head_direct<CODEC_U8><<<grid, 256, 0, st>>>(p); break;

@@ -17,6 +17,10 @@ struct HeadParams {
     float2* out;               // [C][out_stride]
     int64_t out_stride;
     int64_t out_mg0;           // decimated index of out[.][0]
+    // optional scratch [C][mixed_stride] for the mixed samples 0 .. (last row) * decim: with many channels and long
+    // filters every row re-mixing its own window is 26x the work (256 channels, 53 rows: 230 M float64 sincos)
+    float2* mixed;
+    int64_t mixed_stride;
 };
 
 int launch_unpack_mix(const void* d_raw, int64_t n, int codec, int iq_order, double phase, double w,
