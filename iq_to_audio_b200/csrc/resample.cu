@@ -16,6 +16,7 @@
 // channel), the point of this stage is removing the second ffmpeg subprocess, not throughput.
 #include <cmath>
 #include <numeric>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -164,20 +165,36 @@ int iq2a_resampler_create(int32_t in_rate, int32_t out_rate, int32_t n_channels,
     num /= g2; den /= g2;
     while (den < (1 << 20) && num < (1 << 20)) { den *= 2; num *= 2; }
     r->g.src_incr = num; r->g.dst_incr = den;
-    std::vector<double> bank((size_t)pc * fl);
-    double norm0 = 0.0;
-    for (int ph = 0; ph < pc; ++ph)
-        for (int i = 0; i < fl; ++i) {
-            const double t = (double)(i - r->g.center) - (double)ph / pc;
-            const double x = M_PI * t * factor;
-            double y = x == 0.0 ? 1.0 : std::sin(x) / x;
-            const double w = 2.0 * std::fabs(t) / fl;
-            y *= bessel_i0(beta * std::sqrt(std::max(1.0 - w * w, 0.0)));
-            bank[(size_t)ph * fl + i] = y;
-            if (ph == 0) norm0 += y;
-        }
-    std::vector<float> bankf(bank.size());
-    for (size_t i = 0; i < bank.size(); ++i) bankf[i] = (float)(bank[i] / norm0);
+    // the filter bank depends on the two rates only: 1024 x 66 Kaiser-windowed sinc values take ~20 ms to build, and
+    // a run opens one resampler per target, so the last one built is kept
+    static std::mutex cache_mu;
+    static std::vector<float> cache_bank;
+    static int cache_in = 0, cache_out = 0;
+    std::vector<float> bankf;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (cache_in == in_rate && cache_out == out_rate && cache_bank.size() == (size_t)pc * fl) bankf = cache_bank;
+    }
+    if (bankf.empty()) {
+        std::vector<double> bank((size_t)pc * fl);
+        double norm0 = 0.0;
+        for (int ph = 0; ph < pc; ++ph)
+            for (int i = 0; i < fl; ++i) {
+                const double t = (double)(i - r->g.center) - (double)ph / pc;
+                const double x = M_PI * t * factor;
+                double y = x == 0.0 ? 1.0 : std::sin(x) / x;
+                const double w = 2.0 * std::fabs(t) / fl;
+                y *= bessel_i0(beta * std::sqrt(std::max(1.0 - w * w, 0.0)));
+                bank[(size_t)ph * fl + i] = y;
+                if (ph == 0) norm0 += y;
+            }
+        bankf.resize(bank.size());
+        for (size_t i = 0; i < bank.size(); ++i) bankf[i] = (float)(bank[i] / norm0);
+        std::lock_guard<std::mutex> lk(cache_mu);
+        cache_bank = bankf;
+        cache_in = in_rate;
+        cache_out = out_rate;
+    }
     if (cudaMalloc(&r->d_bank, bankf.size() * sizeof(float)) != cudaSuccess ||
         cudaMemcpy(r->d_bank, bankf.data(), bankf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -150,8 +150,16 @@ def choose_mix_sign(warmup: np.ndarray, sample_rate: float, freq_offset: float, 
     Both candidate signs are run as two channels of one bank over the warm-up snippet; the
     mean power of the settled channel samples is compared in float64 on the host, with the
     reference's tie-break (strictly greater wins, +1 first)."""
+    return choose_mix_signs(warmup, sample_rate, [freq_offset], taps, decimation, device=device)[0]
+
+
+def choose_mix_signs(warmup: np.ndarray, sample_rate: float, freq_offsets, taps: np.ndarray,
+                     decimation: int, *, device: int | None = None) -> list[int]:
+    """`choose_mix_sign` for several targets at once: all 2 x T candidates are channels of ONE bank (a bank per
+    target costs ~40 ms of set-up and tear-down each, more than the probing itself)."""
+    offsets = [float(f) for f in freq_offsets]
     if warmup.size == 0:
-        return 1
+        return [1] * len(offsets)
     from .bank import ChannelBank, Target
     span = max(int(sample_rate * 0.05), len(taps) * 4, 131_072)
     take = min(warmup.size, span)
@@ -160,18 +168,21 @@ def choose_mix_sign(warmup: np.ndarray, sample_rate: float, freq_offset: float, 
     snippet = np.ascontiguousarray(warmup[:take], dtype=np.complex64)
     d = max(decimation, 1)
     cands = (1, -1)
-    with ChannelBank(sample_rate, d, [Target(freq_offset, taps, s, "iq") for s in cands],
+    with ChannelBank(sample_rate, d, [Target(off, taps, s, "iq") for off in offsets for s in cands],
                      codec="complex64", ref_chunk=max(take, 1), device=_DEVICE if device is None else int(device)) as bank:
         bb = bank.process_chunk(snippet, want_baseband=True).baseband
-    best_sign, best_power = 1, -np.inf
-    for row, sign in zip(bb, cands):
-        if row.size == 0:
-            power = -np.inf
-        else:
-            settled = row[min(len(taps), row.size // 4):]
-            if settled.size == 0:
-                settled = row
-            power = float(np.mean(np.abs(settled.astype(np.complex128)) ** 2))
-        if power > best_power:
-            best_power, best_sign = power, sign
-    return best_sign
+    signs = []
+    for t in range(len(offsets)):
+        best_sign, best_power = 1, -np.inf
+        for row, sign in zip(bb[2 * t:2 * t + 2], cands):
+            if row.size == 0:
+                power = -np.inf
+            else:
+                settled = row[min(len(taps), row.size // 4):]
+                if settled.size == 0:
+                    settled = row
+                power = float(np.mean(np.abs(settled.astype(np.complex128)) ** 2))
+            if power > best_power:
+                best_power, best_sign = power, sign
+        signs.append(best_sign)
+    return signs
