@@ -293,7 +293,10 @@ class ClockSampler:
             self._stop.wait(self.period)
 
     def __enter__(self):
+        # re-entrant: the resident and the end-to-end timed regions both add samples (one NVML query takes several
+        # milliseconds on these boxes, so the 20 ms resident region alone yields one or two)
         if self.nv is not None:
+            self._stop.clear()
             self._thr = threading.Thread(target=self._loop, daemon=True)
             self._thr.start()
         return self
@@ -667,12 +670,13 @@ def main() -> None:
                 bytes_out += r.audio.nbytes + r.clipped.nbytes
         e2e_step()
         sync_all()
-        t0 = time.perf_counter()
         reps = max(1, min(steps, 3))
-        for _ in range(reps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+        with sampler:
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
         e2e_rank_ms = [e2e_ms]
         if world > 1:
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)

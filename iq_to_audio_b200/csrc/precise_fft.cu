@@ -74,16 +74,18 @@ __device__ __forceinline__ void ddif(double2 (&v)[32], const double2* __restrict
 
 // In-place forward 1024-point transforms of `ncol` columns of the tile (element n of column c at s[n*kRS + c]).
 // X[k] ends up in row (k & 31) * 32 + (k >> 5).
-__device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restrict__ tw, int ncol) {
+// `load(i)` supplies element n = g + 32 i of this thread's column (c, g = thread & 3, thread / 4): from the tile itself
+// (the inverse transform) or straight from global memory (the forward tiles: no staging pass through shared memory).
+template <class Load>
+__device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restrict__ tw, int ncol, Load&& load) {
     const int c = threadIdx.x & (kCols - 1), g = threadIdx.x / kCols;        // g: 0..31
     double2 v[32];
     if (c < ncol) {
         // pass 1: n = m2 + 32 m1, 32-point DIF over m1 for m2 = g, then W_1024^{m2 k1}; result k1 -> row k1*32 + m2
-        double2* col = s + (size_t)g * kRS + c;
-        sfor<32>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = col[(size_t)i * 32 * kRS]; });
+        sfor<32>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = load(i); });
         ddif<32, 0>(v, tw);
     }
-    __syncthreads();
+    __syncthreads();                          // every thread is done with the tile's previous contents
     if (c < ncol) {
         sfor<32>([&](auto kc) {
             constexpr int k1 = decltype(kc)::value;
@@ -104,6 +106,10 @@ __device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restri
         sfor<32>([&](auto kc) { constexpr int k2 = decltype(kc)::value; row[(size_t)k2 * kRS] = v[rev5(k2)]; });
     }
     __syncthreads();
+}
+__device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restrict__ tw, int ncol) {
+    const double2* col = s + (size_t)(threadIdx.x / kCols) * kRS + (threadIdx.x & (kCols - 1));
+    fft1024_tile(s, tw, ncol, [&](int i) { return col[(size_t)i * 32 * kRS]; });
 }
 
 __global__ void k_fir_fftr_build(const double* __restrict__ taps, int ntaps, int D, int Q,
@@ -147,20 +153,17 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
 #pragma unroll
     for (int i = 0; i < kBins; ++i) acc[i] = make_double2(0.0, 0.0);
     __syncthreads();
+    const int tc = threadIdx.x & (kCols - 1), tg = threadIdx.x / kCols;
     for (int p0 = 0; p0 < D; p0 += kCols) {
         const int ncol = min(kCols, D - p0);
-        for (int idx = threadIdx.x; idx < kM * kCols; idx += kThreads) {
-            const int j = idx / kCols, c = idx % kCols;
-            const int64_t sr = row0 + j;
-            double2 v = make_double2(0.0, 0.0);
-            if (c < ncol && sr < src_rows) {
-                const float2 f = mixed[sr * (int64_t)D + p0 + c];
-                v = make_double2((double)f.x, (double)f.y);
-            }
-            s[(size_t)j * kRS + c] = v;
-        }
-        __syncthreads();
-        fft1024_tile(s, tw, ncol);
+        // the 32 rows this thread transforms in pass 1 come straight from global memory (the four columns of a row
+        // are one 32-byte sector); rows past the end of the signal are zero
+        const float2* __restrict__ src = mixed + (row0 + tg) * (int64_t)D + p0 + tc;
+        fft1024_tile(s, tw, ncol, [&](int i) {
+            float2 f = make_float2(0.f, 0.f);
+            if (row0 + tg + 32 * i < src_rows) f = __ldg(src + (int64_t)(32 * i) * D);
+            return make_double2((double)f.x, (double)f.y);
+        });
 #pragma unroll
         for (int i = 0; i < kBins; ++i) {
             const int rho = threadIdx.x + i * kThreads;
