@@ -100,8 +100,12 @@ def other_workload_specs():
          [(2.3e6, "am", 10_000.0, True), (-4.1e6, "usb", 2_800.0, True), (6.2e6, "lsb", 2_800.0, True)], False),
         ("cfg4", "61.44 MS/s, 5 NFM targets, one 10 s time shard per GPU (halo + recurrence warm-up), audio to "
                  "per-target writers over NCCL", 61.44e6, 10.0, nfm([-21.3e6, -9.7e6, 1.9e6, 12.4e6, 25.1e6]), True),
-        ("cfg5_c16", "wideband sweep point: 61.44 MS/s, 16 NFM channels on a uniform grid", 61.44e6, 2.0, nfm(grid(16)), False),
-        ("cfg5_c256", "wideband sweep point: 61.44 MS/s, 256 NFM channels on a uniform grid", 61.44e6, 1.0, nfm(grid(256)), False),
+        # (BASELINE configs[4] also sweeps the reference's filter block 16k-256k: this path has no such parameter -- the
+        # hop is the M - Vd rows of the polyphase bank's 512-point transforms -- so only the channel axis exists here)
+        ("cfg5_c16", "wideband sweep point: 61.44 MS/s, 16 NFM channels on a uniform grid (filter_block n/a: hop = M - Vd rows)",
+         61.44e6, 2.0, nfm(grid(16)), False),
+        ("cfg5_c256", "wideband sweep point: 61.44 MS/s, 256 NFM channels on a uniform grid (filter_block n/a: hop = M - Vd rows)",
+         61.44e6, 1.0, nfm(grid(256)), False),
     ]
 
 

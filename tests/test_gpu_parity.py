@@ -217,10 +217,11 @@ def test_stream_case_c_am_usb_lsb_with_agc(gpu):
     for i in (1, 2):
         g = gold[i]
         assert counts == list(g["counts"])
-        assert np.mean(cat["bb"][i] == g["baseband"]) > 0.999            # bit-identical channel samples
+        assert np.mean(cat["bb"][i] == g["baseband"]) > 0.99999          # bit-identical channel samples
         assert np.abs(cat["clipped"][i] - g["clipped"]).max() <= AUDIO_TOL
-        assert np.abs(cat["audio"][i] - g["audio"]).max() <= AUDIO_TOL * max(1.0, float(g["peak"]))
-        assert abs(peaks[i] - float(g["peak"])) <= AUDIO_TOL * float(g["peak"])
+        # the AGC output reaches ~58 before the clip: held to 1e-4 ABSOLUTE (measured: every sample is bit-identical)
+        assert np.abs(cat["audio"][i] - g["audio"]).max() <= AUDIO_TOL
+        assert abs(peaks[i] - float(g["peak"])) <= AUDIO_TOL
         assert np.abs(rms[:, i] - g["rms_dbfs"]).max() <= 1e-3
 
 
@@ -243,7 +244,7 @@ def test_resident_case_c_agc_chunks_in_parallel(gpu):
     for i, g in enumerate(gold):
         assert k == g["audio"].size
         assert np.abs(c[i] - g["clipped"]).max() <= AUDIO_TOL
-        assert np.abs(a[i] - g["audio"]).max() <= AUDIO_TOL * max(1.0, float(g["peak"]))
+        assert np.abs(a[i] - g["audio"]).max() <= AUDIO_TOL                   # absolute, also for the AGC's ~58 peaks
         assert np.abs(rms[i] - g["rms_dbfs"]).max() <= 1e-3
 
 
