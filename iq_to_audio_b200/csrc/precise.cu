@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "fft64.cuh"
 #include "precise.cuh"
+#include "sincos_cw.cuh"
 #include "../../include/iq2a_b200.h"
 
 namespace iq2a {
@@ -35,35 +36,69 @@ __device__ __forceinline__ float2 cmul_np2(float2 a, float2 b) {   // numpy comp
 }
 
 // ---------------------------------------------------------------------------------------
+constexpr int kMixPer = 4;             // samples per thread: the index arithmetic and parameter loads are paid once
+
 template <int FMT>
 __global__ void __launch_bounds__(256) k_mix_exact(const MixExactParams p) {
     using raw_t = typename RawT<FMT>::type;
-    const raw_t* rp = reinterpret_cast<const raw_t*>(p.raw);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.count) return;
-    const int64_t n = p.n0 + i;
-    float2 out = make_float2(0.f, 0.f);
-    const int64_t f = n - p.raw_n0;
-    if (n >= 0 && f >= 0 && f < p.raw_len) {
-        const float2 x = raw_to_c64<FMT>(rp[f], p.iq_swap, p.q_neg);
-        double ph;
-        if (n >= p.phase.seg0_n || p.nhist == 0) {
-            ph = nco_phase(p.phase, p.chan, p.w, n);
-        } else {
-            int i = p.nhist - 1;
-            while (i > 0 && n < p.hist_start[i]) --i;
-            ph = __dadd_rn(p.hist_phase[i], __dmul_rn(p.w, (double)(n - p.hist_start[i])));
-        }
-        double s, c;
-        sincos(ph, &s, &c);
-        out = cmul_np2(x, make_float2((float)c, (float)s));
+    const raw_t* __restrict__ rp = reinterpret_cast<const raw_t*>(p.raw);
+    const int64_t base = (int64_t)blockIdx.x * (256 * kMixPer);
+    // nco_phase() finds the phase-table segment of a sample with a 64-bit division (~90 instructions; with the index
+    // arithmetic of a one-sample thread the kernel ran ~200 instructions per sample and was issue-bound): the samples
+    // of a CTA are consecutive, so the division is done once per CTA and a thread only steps over the (at most one)
+    // segment boundary inside the CTA
+    __shared__ int64_t s_k0;
+    const int64_t seg_len = p.phase.seg_len, seg0 = p.phase.seg0_n;
+    const int nseg = p.phase.nseg;
+    const bool one_boundary = seg_len >= (int64_t)(256 * kMixPer);
+    if (threadIdx.x == 0) {
+        const int64_t rel0 = p.n0 + base - seg0;
+        int64_t k = rel0 < 0 ? 0 : rel0 / seg_len;
+        if (k >= nseg) k = nseg - 1;
+        s_k0 = k;
     }
-    p.mixed[i] = out;
+    __syncthreads();
+    const int64_t k0 = s_k0;
+    const double* __restrict__ tab = p.phase.tab + (int64_t)p.chan * nseg;
+    const double t0 = tab[k0], t1 = tab[k0 + 1 < nseg ? k0 + 1 : k0];
+    const int64_t rel_k0 = k0 * seg_len;
+#pragma unroll
+    for (int j = 0; j < kMixPer; ++j) {
+        const int64_t i = base + threadIdx.x + j * 256;           // coalesced per j
+        if (i >= p.count) break;
+        const int64_t n = p.n0 + i;
+        float2 out = make_float2(0.f, 0.f);
+        const int64_t f = n - p.raw_n0;
+        if (n >= 0 && f >= 0 && f < p.raw_len) {
+            const float2 x = raw_to_c64<FMT>(rp[f], p.iq_swap, p.q_neg);
+            double ph;
+            if ((n >= seg0 || p.nhist == 0) && one_boundary) {
+                const int64_t rel = n - seg0;
+                int64_t local = rel - rel_k0;
+                double tb = t0;
+                if (rel >= 0 && local >= seg_len && k0 < nseg - 1) {
+                    local -= seg_len;
+                    tb = t1;
+                }
+                ph = __dadd_rn(tb, __dmul_rn(p.w, (double)local));
+            } else if (n >= seg0 || p.nhist == 0) {
+                ph = nco_phase(p.phase, p.chan, p.w, n);
+            } else {
+                int h = p.nhist - 1;
+                while (h > 0 && n < p.hist_start[h]) --h;
+                ph = __dadd_rn(p.hist_phase[h], __dmul_rn(p.w, (double)(n - p.hist_start[h])));
+            }
+            double sn, cs;
+            sincos_cw(ph, &sn, &cs);       // within 1 ulp of sincos(), a third of its instructions at these arguments
+            out = cmul_np2(x, make_float2((float)cs, (float)sn));
+        }
+        p.mixed[i] = out;
+    }
 }
 
 int launch_mix_exact(const MixExactParams& p, int codec, cudaStream_t st) {
     if (p.count <= 0) return IQ2A_OK;
-    const unsigned grid = (unsigned)((p.count + 255) / 256);
+    const unsigned grid = (unsigned)((p.count + 256 * kMixPer - 1) / (256 * kMixPer));
     switch (codec) {
         case CODEC_S16: k_mix_exact<CODEC_S16><<<grid, 256, 0, st>>>(p); break;
         case CODEC_U8: k_mix_exact<CODEC_U8><<<grid, 256, 0, st>>>(p); break;
