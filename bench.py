@@ -522,8 +522,11 @@ def main() -> None:
         k = kk % len(audio_bufs)
         audio = audio_bufs[k]
         if world == 1:
-            bank.process_resident(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
-                                  warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows)
+            # device-side ordering only, like the multi-GPU arm: the host enqueues ahead and the timed region ends with a
+            # synchronize (the synchronous call left the GPU idle for the launch latency of every step)
+            bank.process_resident_async(capture.data_ptr(), first, seg_end - first + d, seg_begin, seg_end,
+                                        warmup_rows=warm_rows, dev_audio=audio.data_ptr(), out_stride=rows,
+                                        stream=comp.cuda_stream)
             return
         # multi-GPU: device-side ordering only, the host runs ahead
         with torch.cuda.stream(comp):
