@@ -441,6 +441,35 @@ __global__ void __launch_bounds__(kFusedThreads) k_tail_fused(const TailParams p
         }
         const int64_t emit_lo = max(t0, p.n_skip);
         double ss_a = 0.0, ss_b = 0.0;
+        if (r0 >= emit_lo && r0 + 3 < t1 && r0 + 3 < p.n - 1 && (r0 + 3 < split || r0 >= split)) {
+            // interior rows (all four emitted, one statistics window, not the capture's last row): no per-row tests
+            float y4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double v_new = fma(a, v, b[i]);
+                y4[i] = deemph ? (float)(ch.beta * (double)x[1 + i] + v) : (float)v_new;
+                v = v_new;
+            }
+            const int64_t o = r0 - p.n_skip;
+            if (p.audio) {
+                float* q = p.audio + (size_t)c * p.out_stride + o;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = y4[i];
+            }
+            if (p.clipped) {
+                float* q = p.clipped + (size_t)c * p.out_stride + o;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = fminf(fmaxf(y4[i], -0.99f), 0.99f);               // processing.py:452
+            }
+            double ss = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                peak = fmaxf(peak, fabsf(y4[i]));
+                ss += (double)y4[i] * (double)y4[i];          // same order of additions as the general loop below
+            }
+            if (r0 < split) ss_a = ss;
+            else ss_b = ss;
+        } else
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t r = r0 + i;
