@@ -45,6 +45,10 @@ static int dev_alloc(T** p, size_t count) {
     }
     return IQ2A_OK;
 }
+// channels per multiply-accumulate CTA of the many-channel form: the spectra of a block set are read from L2 once per
+// group, so larger groups mean less traffic; 5 is what fits 128 registers without spills (6 spills 412 bytes)
+constexpr int kManyGroup = 5;
+
 template <typename T>
 static int dev_grow(T** p, size_t* cap, size_t need) {
     if (need <= *cap) return IQ2A_OK;
@@ -137,7 +141,7 @@ struct iq2a_bank {
     int* d_repaired = nullptr;
     float2* d_gtab2 = nullptr;      // layout/scale of the second-generation kernel (int16, M=512, D%4==0)
     int* d_setctr = nullptr;        // block-set counter of the generation-5 kernel (dynamic scheduling)
-    // many-channel form (channelizer5s.cuh): forward transforms once per wave of block sets, groups of <= 4 channels
+    // many-channel form (channelizer5s.cuh): forward transforms once per wave of block sets, groups of <= 5 channels
     bool many_ok = false;
     // low-rate captures (D = 1..2 with 1025+ taps: more history rows than any transform size holds): every channel's
     // samples come from the float64 mixer + direct-form filter of the bit-faithful path; `exact` lists the channels
@@ -330,7 +334,7 @@ static int run_core(iq2a_bank* b, const CoreArgs& a) {
         sp.rot = b->d_rot;
         sp.phase_tab = b->d_phase;
         sp.out = b->d_bb;
-        if ((rc = launch_channelize5_many(p, geo, t_base, t_row0, t_rows, sp, (int)b->groups.size(), 4, wave, b->n_sm, a.st, &b->launches))) return rc;
+        if ((rc = launch_channelize5_many(p, geo, t_base, t_row0, t_rows, sp, (int)b->groups.size(), kManyGroup, wave, b->n_sm, a.st, &b->launches))) return rc;
         b->launches_v2++;
     }
     for (const Group& g : b->groups) {
@@ -709,7 +713,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
     // each run in groups of <= gmax channels -- so that a group can take the mirror-pair kernel with its own geometry
     // and a group of bit-faithful channels is not computed twice; too many runs: plain groups of consecutive channels
     // 25+ channels of one filter on the int16 / TMA path (5+ launches of the fused kernel): the many-channel form, whose multiply-accumulate kernel
-    // takes groups of <= 4 channels (IQ2A_MANY=0 keeps the fused kernel)
+    // takes groups of <= 5 channels (IQ2A_MANY=0 keeps the fused kernel)
     bool many = false;
     {
         const char* env = std::getenv("IQ2A_CHANNELIZER");
@@ -720,7 +724,7 @@ int iq2a_bank_create(const iq2a_bank_config* cfg, const iq2a_channel_desc* ch, i
         PairGeo probe{};
         many = many && pair_geometry(tn[0], D, &probe);
     }
-    const int gmax = many ? 4 : channelize_max_group(M);
+    const int gmax = many ? kManyGroup : channelize_max_group(M);
     size_t g_total = 0;
     {
         std::vector<std::pair<int, int>> runs;                 // (first, count)

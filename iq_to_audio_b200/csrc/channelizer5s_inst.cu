@@ -47,6 +47,7 @@ int launch_channelize5_split(const ChannelizeParams& p, const PairMaps& maps, co
             case 2: rc = launch_mac5<2>(p, geo, sp, ngroups, st); break;
             case 3: rc = launch_mac5<3>(p, geo, sp, ngroups, st); break;
             case 4: rc = launch_mac5<4>(p, geo, sp, ngroups, st); break;
+            case 5: rc = launch_mac5<5>(p, geo, sp, ngroups, st); break;
             default: set_error("split channel bank: unsupported group size %d", cg_max); return IQ2A_ERR_INVALID;
         }
         if (rc) return rc;

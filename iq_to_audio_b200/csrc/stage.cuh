@@ -49,7 +49,7 @@ int launch_channelize2(const ChannelizeParams& p, int cg, const void* base, int6
 bool pair_geometry(int ntaps, int D, PairGeo* geo);
 int launch_channelize5(const ChannelizeParams& p, int cg, const PairGeo& geo, const void* base, int64_t tmap_row0,
                        int64_t rows, int n_sm, cudaStream_t st);
-// many-channel form: forward transforms once per wave of block sets, then every channel group (<= 4 channels each)
+// many-channel form: forward transforms once per wave of block sets, then every channel group (<= 5 channels each)
 int launch_channelize5_many(const ChannelizeParams& p, const PairGeo& geo, const void* base, int64_t tmap_row0, int64_t rows,
                             const SplitParams& sp, int ngroups, int cg_max, int wave_sets, int n_sm, cudaStream_t st, int64_t* launches);
 size_t channelize5_scratch_bytes_per_set(const PairGeo& geo);
