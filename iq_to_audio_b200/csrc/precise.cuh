@@ -72,10 +72,10 @@ struct FirFftPlan {
     int* risky = nullptr;           // rows to recompute by the direct form
     size_t risky_cap = 0;
     int* n_risky = nullptr;         // [0]: entries of `risky` in the current launch, [1]: total repaired so far
-    // distance to a float32 rounding boundary below which a sample is recomputed: ~30x the transform's error
-    // (tools/precise_tol_sweep.py: with NO repair 1 of 322 640 components differs from the direct form and that one
-    // lies within 1e-15 of its boundary; IQ2A_PRECISE_TOL overrides)
-    double tol = 3e-14;
+    // distance to a float32 rounding boundary below which a sample is recomputed: tol + tol_rel |v| (precise_fft.cu
+    // header; IQ2A_PRECISE_TOL / IQ2A_PRECISE_TOL_REL override)
+    double tol = 1e-15;
+    double tol_rel = 64.0 * 1.1102230246251565e-16;
 };
 int fir_fft_plan_create(FirFftPlan* plan, const double* d_taps, int ntaps, int D, int Q, cudaStream_t st);
 void fir_fft_plan_destroy(FirFftPlan* plan);

@@ -13,9 +13,14 @@
 //                  multiply-accumulate reads it coalesced.  Every output whose float64 value lies within `tol` of the
 //                  midpoint between two float32 values is appended to a repair list.
 //   k_fir_repair   one CTA per listed sample: the float64 direct form over all taps (the sum precise.cu computes),
-//                  rounded once.  4 tol / ulp(|s|) of the samples: 1e-5 at |s| ~ 0.1, 0.4 % for a channel 50 dB down.
-// A sample that is NOT listed is at least `tol` = 3e-14 away from any rounding boundary, ~30x the transform's error
-// (measured: tools/precise_tol_sweep.py), so its float32 rounding is the direct form's.
+//                  rounded once.  4 tol / ulp(|s|) of the samples are listed.
+// tol(v) = tol_abs + tol_rel |v| = 1e-15 + 64 eps |v|.  Measured (tools/precise_tol_sweep.py, 20 s at int16 full scale,
+// 3.8 M samples per channel): with NO repair the transform form adds ONE differing sample to the three that two
+// float64 direct forms with different summation orders already disagree on (values within ~1e-17 of a rounding
+// boundary, which no float64 evaluation -- the reference's included -- can decide), i.e. its error in a channel 60 dB
+// below the wideband level is ~1e-17, 100x below tol_abs; the relative term covers strong channels, where the
+// transform's error follows the signal (a few eps |v|).  Round 2 started with a flat 3e-14 (0.8 % of the rows of a
+// quiet channel listed, 2.7 of 12 ms on cfg3's shape).
 #include <cstdlib>
 #include <utility>
 
@@ -140,7 +145,7 @@ __device__ __forceinline__ double boundary_distance(double v) {
 
 __global__ void __launch_bounds__(kThreads, 2)
 k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, const double2* __restrict__ tw_g, int D, int Q,
-             int64_t nrows, float2* __restrict__ out, double tol, int* __restrict__ risky, int* __restrict__ n_risky,
+             int64_t nrows, float2* __restrict__ out, double tol, double tol_rel, int* __restrict__ risky, int* __restrict__ n_risky,
              int risky_cap) {
     extern __shared__ __align__(16) unsigned char sm[];
     double2* s = reinterpret_cast<double2*>(sm);                          // [kM][kRS]
@@ -192,7 +197,7 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
             const double2 v = s[(size_t)((j & 31) * 32 + (j >> 5)) * kRS];
             const double re = v.x, im = -v.y;
             out[m] = make_float2((float)re, (float)im);
-            if (boundary_distance(re) < tol || boundary_distance(im) < tol) {
+            if (boundary_distance(re) < fma(fabs(re), tol_rel, tol) || boundary_distance(im) < fma(fabs(im), tol_rel, tol)) {
                 const int at = atomicAdd(n_risky, 1);
                 if (at < risky_cap) risky[at] = (int)m;
             }
@@ -265,6 +270,7 @@ int fir_fftr_plan_create(FirFftPlan* pl, const double* d_taps, int ntaps, int D,
     pl->taps = d_taps;
     pl->reg = true;
     if (const char* env = std::getenv("IQ2A_PRECISE_TOL")) pl->tol = std::atof(env);
+    if (const char* env = std::getenv("IQ2A_PRECISE_TOL_REL")) pl->tol_rel = std::atof(env);
     IQ2A_CUDA_TRY(cudaMalloc(&pl->tw, (size_t)kM * sizeof(double2)));
     IQ2A_CUDA_TRY(cudaMalloc(&pl->H, (size_t)D * kM * sizeof(double2)));
     IQ2A_CUDA_TRY(cudaMalloc(&pl->n_risky, 2 * sizeof(int)));
@@ -295,7 +301,7 @@ int launch_fir_fft64r(FirFftPlan& pl, const float2* d_mixed, int64_t nrows, floa
     IQ2A_CUDA_TRY(cudaMemsetAsync(pl.n_risky, 0, sizeof(int), st));
     const int ld = kM - pl.Q;
     const unsigned grid = (unsigned)((nrows + ld - 1) / ld);
-    k_fir_fft64r<<<grid, kThreads, kSmem, st>>>(d_mixed, pl.H, pl.tw, pl.D, pl.Q, nrows, d_out, pl.tol, pl.risky, pl.n_risky,
+    k_fir_fft64r<<<grid, kThreads, kSmem, st>>>(d_mixed, pl.H, pl.tw, pl.D, pl.Q, nrows, d_out, pl.tol, pl.tol_rel, pl.risky, pl.n_risky,
                                                 (int)pl.risky_cap);
     k_fir_repair<<<592, kRepairThreads, 0, st>>>(d_mixed, pl.taps, pl.ntaps, pl.D, pl.Q, pl.risky, pl.n_risky, (int)pl.risky_cap, d_out);
     IQ2A_CUDA_TRY(cudaGetLastError());

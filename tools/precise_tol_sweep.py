@@ -31,7 +31,8 @@ def child(seconds: float) -> None:
     chunk = 8 << 20
     n = max(chunk, int(seconds * fs) // chunk * chunk)
     # a strong tone in one SSB channel, noise only in the other (the quiet channel is the hard case: small |s|)
-    raw = bench.synth_capture_device(0, n + d, dev, 5, fs, [(-4.1e6, "usb", 900.0, 0.2), (2.3e6, "am", 700.0, 0.2)],
+    amp = float(os.environ.get("SWEEP_AMP", "0.2"))      # 0.2: the bench's level; 0.45: close to int16 full scale
+    raw = bench.synth_capture_device(0, n + d, dev, 5, fs, [(-4.1e6, "usb", 900.0, amp), (2.3e6, "am", 700.0, amp)],
                                      noise=float(os.environ.get("SWEEP_NOISE", "0.02")))
     tg = [Target(-4.1e6, design_channel_filter(fs, 2_800.0, d), 1, "usb", 300.0, True),
           Target(6.2e6, design_channel_filter(fs, 2_800.0, d), 1, "lsb", 300.0, True)]
@@ -55,17 +56,20 @@ def main() -> None:
     ap.add_argument("--child", action="store_true")
     ap.add_argument("--noise", type=float, default=0.02, help="wideband noise per component (the quiet channel's level)")
     ap.add_argument("--tols", default="1e-12,1e-13,1e-14,3e-15,1e-15,0")
+    ap.add_argument("--amp", type=float, default=0.2, help="amplitude of the two strong carriers (wideband level)")
     a = ap.parse_args()
     if not a.child:
         os.environ["SWEEP_NOISE"] = str(a.noise)
+        os.environ["SWEEP_AMP"] = str(a.amp)
     if a.child:
         child(a.seconds)
         return
     import numpy as np
     out = {}
     ref = None
-    for label, env in [("direct", {"IQ2A_PRECISE_FIR": "direct"})] + [(f"tol={t}", {"IQ2A_PRECISE_TOL": t}) for t in
-                                                                        a.tols.split(",")]:
+    for label, env in [("direct", {"IQ2A_PRECISE_FIR": "direct"})] + \
+            [("default", {}) if t == "default" else (f"tol={t}", {"IQ2A_PRECISE_TOL": t, "IQ2A_PRECISE_TOL_REL": "0"})
+             for t in a.tols.split(",")]:
         path = f"/tmp/sweep_{label.replace('=', '_')}.npy"
         r = subprocess.run([sys.executable, __file__, "--child", "--seconds", str(a.seconds)], capture_output=True, text=True,
                            env={**os.environ, **env, "SWEEP_OUT": path})
