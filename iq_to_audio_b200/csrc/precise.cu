@@ -62,6 +62,30 @@ __global__ void __launch_bounds__(256) k_mix_exact(const MixExactParams p) {
     const double* __restrict__ tab = p.phase.tab + (int64_t)p.chan * nseg;
     const double t0 = tab[k0], t1 = tab[k0 + 1 < nseg ? k0 + 1 : k0];
     const int64_t rel_k0 = k0 * seg_len;
+    {
+        // interior CTAs (all samples present, one phase-table segment, no history rows): no per-sample tests, 32-bit
+        // index arithmetic -- 64-bit compares, conversions and bounds tests were half of the general loop below
+        const int64_t n_first = p.n0 + base, n_last = n_first + 256 * kMixPer - 1;
+        const int64_t l_first = n_first - seg0 - rel_k0;
+        const bool fast = one_boundary && base + 256 * kMixPer <= p.count && n_first >= seg0 && n_first >= 0 &&
+                          n_first >= p.raw_n0 && n_last - p.raw_n0 < p.raw_len && l_first >= 0 &&
+                          l_first + 256 * kMixPer < (int64_t)0x7fffffff && (l_first + 256 * kMixPer <= seg_len || k0 == nseg - 1);
+        if (fast) {
+            const raw_t* __restrict__ src = rp + (n_first - p.raw_n0) + threadIdx.x;
+            float2* __restrict__ dst = p.mixed + base + threadIdx.x;
+            const int l0 = (int)l_first + (int)threadIdx.x;
+            const double w = p.w;
+#pragma unroll
+            for (int j = 0; j < kMixPer; ++j) {
+                const float2 x = raw_to_c64<FMT>(src[j * 256], p.iq_swap, p.q_neg);
+                const double ph = __dadd_rn(t0, __dmul_rn(w, (double)(l0 + j * 256)));
+                double sn, cs;
+                sincos_cw(ph, &sn, &cs);
+                dst[j * 256] = cmul_np2(x, make_float2((float)cs, (float)sn));
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < kMixPer; ++j) {
         const int64_t i = base + threadIdx.x + j * 256;           // coalesced per j
