@@ -35,7 +35,7 @@ namespace {
 
 constexpr int kM = 1024;
 constexpr int kCols = 4;                   // branch columns per tile
-constexpr int kRS = kCols + 1;             // tile row stride (double2): conflict-free column reads by consecutive rows
+constexpr int kRS = kCols;                 // tile row stride (double2); bank conflicts are avoided by the swizzle of tix()
 constexpr int kThreads = 128;              // kCols x 32 row groups; 248 registers each -> two CTAs per SM
 constexpr int kBins = kM / kThreads;       // spectrum rows per thread in the multiply-accumulate
 constexpr size_t kTileBytes = (size_t)kM * kRS * sizeof(double2);
@@ -51,6 +51,16 @@ __device__ __forceinline__ void sfor(F&& f) {
 }
 __host__ __device__ constexpr int rev5(int k) {
     return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+// Index of element (row, column) of the tile.  A row is four double2 (64 bytes), two rows share a 128-byte line of
+// eight 16-byte units, and the unit inside the line is XOR-swizzled with ((row >> 1) & 3) | (((row >> 5) & 1) << 2),
+// so that all three access patterns of a quarter-warp (8 threads x 16 bytes = one wavefront) touch eight different
+// units: pass-1 stores (rows g, g+1 x 4 columns), pass-2 loads / stores (rows 32 g + i, 32 (g+1) + i x 4 columns) and
+// the multiply-accumulate's reads (8 consecutive rows, one column).  The padded layout this replaces (row stride 5)
+// served only the last one; the two passes took two wavefronts per quarter-warp (profiles: L1 data pipe 62 %).
+__device__ __forceinline__ int tix(int row, int c) {
+    return ((row << 2) | c) ^ (((row >> 1) & 3) | (((row >> 5) & 1) << 2));
 }
 
 // radix-2 DIF of N points held in v[OFF .. OFF+N), twiddles W_N^j = tw[j * (1024 / N)]; X[k] ends in slot rev(k)
@@ -77,7 +87,7 @@ __device__ __forceinline__ void ddif(double2 (&v)[32], const double2* __restrict
     }
 }
 
-// In-place forward 1024-point transforms of `ncol` columns of the tile (element n of column c at s[n*kRS + c]).
+// In-place forward 1024-point transforms of `ncol` columns of the tile (element n of column c at s[tix(n, c)]).
 // X[k] ends up in row (k & 31) * 32 + (k >> 5).
 // `load(i)` supplies element n = g + 32 i of this thread's column (c, g = thread & 3, thread / 4): from the tile itself
 // (the inverse transform) or straight from global memory (the forward tiles: no staging pass through shared memory).
@@ -99,22 +109,21 @@ __device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restri
                 const double2 w = tw[(g * k1) & (kM - 1)];
                 x = make_double2(fma(x.x, w.x, -x.y * w.y), fma(x.x, w.y, x.y * w.x));
             }
-            s[(size_t)(k1 * 32 + g) * kRS + c] = x;
+            s[tix(k1 * 32 + g, c)] = x;
         });
     }
     __syncthreads();
     if (c < ncol) {
         // pass 2: for k1 = g, 32-point DIF over m2; X[k1 + 32 k2] -> row k1*32 + k2
-        double2* row = s + (size_t)g * 32 * kRS + c;
-        sfor<32>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = row[(size_t)i * kRS]; });
+        sfor<32>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = s[tix(g * 32 + i, c)]; });
         ddif<32, 0>(v, tw);
-        sfor<32>([&](auto kc) { constexpr int k2 = decltype(kc)::value; row[(size_t)k2 * kRS] = v[rev5(k2)]; });
+        sfor<32>([&](auto kc) { constexpr int k2 = decltype(kc)::value; s[tix(g * 32 + k2, c)] = v[rev5(k2)]; });
     }
     __syncthreads();
 }
 __device__ __forceinline__ void fft1024_tile(double2* s, const double2* __restrict__ tw, int ncol) {
-    const double2* col = s + (size_t)(threadIdx.x / kCols) * kRS + (threadIdx.x & (kCols - 1));
-    fft1024_tile(s, tw, ncol, [&](int i) { return col[(size_t)i * 32 * kRS]; });
+    const int c = threadIdx.x & (kCols - 1), g = threadIdx.x / kCols;
+    fft1024_tile(s, tw, ncol, [&](int i) { return s[tix(g + 32 * i, c)]; });
 }
 
 __global__ void k_fir_fftr_build(const double* __restrict__ taps, int ntaps, int D, int Q,
@@ -172,10 +181,9 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
 #pragma unroll
         for (int i = 0; i < kBins; ++i) {
             const int rho = threadIdx.x + i * kThreads;
-            const double2* xs = s + (size_t)rho * kRS;
             const double2* hs = H + (size_t)p0 * kM + rho;
             for (int c = 0; c < ncol; ++c) {
-                const double2 h = hs[(size_t)c * kM], x = xs[c];
+                const double2 h = hs[(size_t)c * kM], x = s[tix(rho, c)];
                 acc[i].x = fma(h.x, x.x, fma(-h.y, x.y, acc[i].x));
                 acc[i].y = fma(h.x, x.y, fma(h.y, x.x, acc[i].y));
             }
@@ -187,14 +195,14 @@ k_fir_fft64r(const float2* __restrict__ mixed, const double2* __restrict__ H, co
     for (int i = 0; i < kBins; ++i) {
         const int rho = threadIdx.x + i * kThreads;
         const int k = (rho >> 5) + 32 * (rho & 31);
-        s[(size_t)k * kRS] = make_double2(acc[i].x, -acc[i].y);
+        s[tix(k, 0)] = make_double2(acc[i].x, -acc[i].y);
     }
     __syncthreads();
     fft1024_tile(s, tw, 1);
     for (int j = Q + threadIdx.x; j < kM; j += kThreads) {
         const int64_t m = row0 + (j - Q);
         if (m < nrows) {
-            const double2 v = s[(size_t)((j & 31) * 32 + (j >> 5)) * kRS];
+            const double2 v = s[tix((j & 31) * 32 + (j >> 5), 0)];
             const double re = v.x, im = -v.y;
             out[m] = make_float2((float)re, (float)im);
             if (boundary_distance(re) < fma(fabs(re), tol_rel, tol) || boundary_distance(im) < fma(fabs(im), tol_rel, tol)) {
