@@ -362,6 +362,8 @@ class PeerWriters:
         return {c: self.recv[s, j] for j, c in enumerate(self.owned)}
 
     def flush(self, last_step: int, stream) -> None:
+        """After the last publish: returns when every rank's pushes of every step have landed on their writers.  The
+        last thing on the side stream is barrier(last_step) across the ranks (signal pads), so waiting for the side
+        stream IS the rendezvous; a host-side collective barrier on top of it only added its own latency."""
         stream.synchronize()
         self.side.synchronize()
-        self.dist.barrier()
